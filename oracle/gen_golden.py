@@ -1,0 +1,259 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the UNMODIFIED reference
+modules (imported from /root/reference/code under oracle/ref_shim.py) on seeded synthetic
+inputs.  Runs only in the build container (the GPU box has no /root/reference); the
+outputs are committed so that every other machine can pin oracle/port.py and the CUDA
+path against what the reference itself computes.
+
+    python -m oracle.gen_golden            # rewrites tests/golden/
+
+What is executed from the reference, unmodified:
+  lib.model.networks.ImplicitNet / RenderingNet   (forward)
+  lib.model.density.LaplaceDensity / AbsDensity
+  lib.model.ray_sampler.ErrorBoundSampler.get_z_vals
+  lib.model.deformer.SMPLDeformer.forward / forward_skinning / query_skinning_weights_smpl_multi, skinning
+  lib.model.multiply.Multiply.sdf_func_with_smpl_deformer / get_rbg_value / forward_gradient /
+      depth2pts_outside / bg_volume_rendering          (called as unbound methods on a shell object)
+  lib.utils.rend_util.get_camera_params / get_sphere_intersections
+and, because Multiply.forward itself needs trimesh (host ray/box test) which is absent, a
+line-for-line driver of its eval branch (multiply.py:223-232, 254-310, 393-418, 425-484,
+514-545, 589-598) that calls those reference objects.
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, port          # noqa: E402
+from multiply_b200 import scene as S       # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_opts(A):
+    imp = A(dict(feature_vector_size=256, d_in=3, d_out=1, dims=[256] * 8, init="geometry", bias=0.6,
+                 skip_in=[4], weight_norm=True, embedder_mode="fourier", multires=6, cond="smpl",
+                 number_person=2, scene_bounding_sphere=3.0))
+    ren = A(dict(feature_vector_size=256, mode="pose_no_view", d_in=14, d_out=3, dims=[256] * 4,
+                 weight_norm=True, multires_view=-1))
+    bgi = A(dict(feature_vector_size=256, d_in=4, d_out=1, dims=[256] * 8, init="none", bias=0.0,
+                 skip_in=[4], weight_norm=False, embedder_mode="fourier", multires=10, cond="frame"))
+    bgr = A(dict(feature_vector_size=256, mode="nerf_frame_encoding", d_in=3, d_out=3, dims=[128],
+                 weight_norm=False, multires_view=4))
+    return imp, ren, bgi, bgr
+
+
+def build_ref_model(ref, scene):
+    """A shell ``Multiply`` object populated with reference sub-modules carrying the synthetic
+    scene's parameters (Multiply.__init__ needs SMPL pkl / betas.npy / smpl_init .pth)."""
+    A = ref.AttrDict
+    imp_o, ren_o, bgi_o, bgr_o = ref_opts(A)
+    Multiply = ref.multiply.Multiply
+    m = Multiply.__new__(Multiply)
+    torch.nn.Module.__init__(m)
+    m.using_nerfacc = True
+    m.use_person_encoder = False
+    m.with_bkgd = True
+    m.sdf_bounding_sphere = 3.0
+    m.foreground_implicit_network_list = torch.nn.ModuleList()
+    m.foreground_rendering_network_list = torch.nn.ModuleList()
+    m.deformer_list = torch.nn.ModuleList()
+    for person in scene["persons"]:
+        net = ref.networks.ImplicitNet(imp_o)
+        net.load_state_dict(person["implicit"], strict=True)
+        m.foreground_implicit_network_list.append(net)
+        rn = ref.networks.RenderingNet(ren_o)
+        rn.load_state_dict(person["render"], strict=True)
+        m.foreground_rendering_network_list.append(rn)
+        D = ref.deformer.SMPLDeformer
+        d = D.__new__(D)
+        torch.nn.Module.__init__(d)
+        d.max_dist, d.K = 0.05, 1
+        d.smpl_verts = person["verts_c"][None]
+        d.smpl_weights = person["weights"][None]
+        m.deformer_list.append(d)
+    m.bg_implicit_network = ref.networks.ImplicitNet(bgi_o)
+    m.bg_implicit_network.load_state_dict(scene["bg_implicit"], strict=True)
+    m.bg_rendering_network = ref.networks.RenderingNet(bgr_o)
+    m.bg_rendering_network.load_state_dict(scene["bg_render"], strict=True)
+    m.density = ref.density.LaplaceDensity(params_init={"beta": scene["beta_param"]}, beta_min=0.0001)
+    m.bg_density = ref.density.AbsDensity()
+    c = scene["cfg"]
+    m.ray_sampler = ref.ray_sampler.ErrorBoundSampler(
+        3.0, inverse_sphere_bg=True, near=c["near"], N_samples=c["N_samples"],
+        N_samples_eval=c["N_samples_eval"], N_samples_extra=c["N_samples_extra"], eps=c["eps"],
+        beta_iters=c["beta_iters"], max_total_iters=c["max_total_iters"],
+        N_samples_inverse_sphere=32, add_tiny=c["add_tiny"])
+    m.eval()
+    return m
+
+
+def ref_forward(ref, m, scene, inputs, hit_lists):
+    """Eval branch of Multiply.forward driven with the reference's own objects."""
+    Multiply = ref.multiply.Multiply
+    torch.set_grad_enabled(True)
+    ray_dirs, cam_loc = ref.rend_util.get_camera_params(inputs["uv"], inputs["pose"], inputs["intrinsics"])
+    _, num_pixels, _ = ray_dirs.shape
+    cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3)
+    ray_dirs = ray_dirs.reshape(-1, 3)
+    P = len(scene["persons"])
+    fg_rgb_list, normal_values_list, sdf_output_list, z_vals_list, person_id_list, z_max_list = [], [], [], [], [], []
+    index_ray_box_list = []
+    trips = []
+    # count sampler trips by wrapping the sdf function
+    for person_id in range(P):
+        person = scene["persons"][person_id]
+        index_ray_box = hit_lists[person_id]
+        if len(index_ray_box) == 0:
+            index_ray_box = torch.tensor([0])
+        index_ray_box = index_ray_box.long()
+        cam_i, dir_i = cam_loc[index_ray_box], ray_dirs[index_ray_box]
+        index_ray_box_list.append(index_ray_box)
+        cond = {"smpl": person["smpl_pose"][:, 3:] / np.pi}
+        smpl_tfs = person["tfs"][None]
+        smpl_verts = person["verts_p"][None]
+        calls = [0]
+        orig = Multiply.sdf_func_with_smpl_deformer
+
+        def counting(self, *a, **k):
+            calls[0] += 1
+            return orig(self, *a, **k)
+        m.sdf_func_with_smpl_deformer = counting.__get__(m)
+        z_vals, _ = m.ray_sampler.get_z_vals(dir_i, cam_i, m, cond, smpl_tfs, eval_mode=True,
+                                             smpl_verts=smpl_verts, person_id=person_id)
+        del m.sdf_func_with_smpl_deformer
+        m.eval()        # the sampler leaves the implicit net in train(); no numeric effect
+        trips.append(calls[0])
+        z_vals, z_vals_bg = z_vals
+        z_max = z_vals[:, -1]
+        z_vals = z_vals[:, :-1]
+        N_samples = z_vals.shape[1]
+        npx = cam_i.shape[0]
+        points = cam_i.unsqueeze(1) + z_vals.unsqueeze(2) * dir_i.unsqueeze(1)
+        points_flat = points.reshape(-1, 3)
+        dirs = dir_i.unsqueeze(1).repeat(1, N_samples, 1)
+        sdf_output, canonical_points, feature_vectors = m.sdf_func_with_smpl_deformer(
+            points_flat, cond, smpl_tfs, smpl_verts=smpl_verts, person_id=person_id)
+        differentiable_points = canonical_points.reshape(npx, N_samples, 3).reshape(-1, 3)
+        sdf_output = sdf_output.reshape(npx, N_samples, 1).reshape(-1, 1)
+        sdf_output_list.append(sdf_output.reshape(npx, N_samples).detach())
+        view = -dirs.reshape(-1, 3)
+        fg_rgb_flat, others = m.get_rbg_value(points_flat, differentiable_points, view, cond, smpl_tfs,
+                                              feature_vectors=feature_vectors, person_id=person_id,
+                                              is_training=False)
+        fg_rgb_list.append(fg_rgb_flat.detach().reshape(-1, N_samples, 3))
+        normal_values_list.append(others["normals"].detach().reshape(-1, N_samples, 3))
+        z_max_list.append(z_max)
+        z_vals_list.append(z_vals)
+        person_id_list.append(torch.ones(npx, N_samples) * person_id)
+
+    # multiply.py:427-480 with the nerfacc restatements of oracle/port.py
+    fg_rgb, normal, acc, acc_p, bg_T = port.composite_nerfacc(
+        index_ray_box_list, z_vals_list, z_max_list, sdf_output_list, fg_rgb_list, normal_values_list,
+        list(range(P)), cam_loc.shape[0], scene["beta_param"])
+    # multiply.py:482-484, 514-539
+    z_vals_bg = m.ray_sampler.inverse_sphere_sampler.get_z_vals(ray_dirs, cam_loc, m)
+    z_vals_bg = z_vals_bg * (1. / m.ray_sampler.scene_bounding_sphere)
+    N_bg = z_vals_bg.shape[1]
+    z_vals_bg = torch.flip(z_vals_bg, dims=[-1, ])
+    bg_dirs = ray_dirs.unsqueeze(1).repeat(1, N_bg, 1)
+    bg_locs = cam_loc.unsqueeze(1).repeat(1, N_bg, 1)
+    bg_points = m.depth2pts_outside(bg_locs, bg_dirs, z_vals_bg)
+    frame_latent_code = scene["frame_code"]
+    with torch.no_grad():
+        bg_output = m.bg_implicit_network(bg_points.reshape(-1, 4), {"frame": frame_latent_code})[0]
+        bg_sdf = bg_output[:, :1]
+        bg_feat = bg_output[:, 1:]
+        bg_ro = m.bg_rendering_network(None, None, bg_dirs.reshape(-1, 3), None, bg_feat, frame_latent_code)
+        bg_rgb = bg_ro.reshape(-1, N_bg, 3)
+        bg_weights = m.bg_volume_rendering(z_vals_bg, bg_sdf)
+        bg_rgb_values = torch.sum(bg_weights.unsqueeze(-1) * bg_rgb, 1)
+    rgb_values = fg_rgb + bg_T.unsqueeze(-1) * bg_rgb_values
+    return dict(acc_map=acc, acc_person_list=acc_p, rgb_values=rgb_values,
+                fg_rgb_values=fg_rgb + bg_T.unsqueeze(-1) * torch.ones_like(fg_rgb),
+                normal_values=normal, bg_T=bg_T, bg_rgb=bg_rgb_values,
+                z_vals=z_vals_list, sdf=sdf_output_list, rgb=fg_rgb_list, normals=normal_values_list,
+                trips=trips)
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().numpy()
+        out[k] = np.asarray(v)
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+def main():
+    torch.set_num_threads(8)
+    ref = ref_shim.load()
+    A = ref.AttrDict
+    scene = S.make_scene(P=2, S=64, seed=42)
+    m = build_ref_model(ref, scene)
+    g = torch.Generator().manual_seed(5)
+
+    # ---- op-level vectors -----------------------------------------------------------
+    p0 = scene["persons"][0]
+    x = (torch.rand(256, 3, generator=g) - 0.5) * 2.0
+    cond = {"smpl": p0["cond"]}
+    with torch.no_grad():
+        y = m.foreground_implicit_network_list[0](x, cond, person_id=0)[0]
+    save("implicit_fg", x=x, out=y)
+
+    xg = x[:64].clone().requires_grad_(True)
+    out = m.foreground_implicit_network_list[0](xg, cond, person_id=0)[0]
+    grad = torch.autograd.grad(out[:, 0].sum(), xg)[0]
+    save("implicit_fg_grad", x=x[:64], grad=grad)
+
+    nrm = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=1)
+    with torch.no_grad():
+        rgb = m.foreground_rendering_network_list[0](x, nrm, None, p0["cond"], y[:, 1:], person_id=0)
+    save("render_fg", x=x, normals=nrm, feat=y[:, 1:], rgb=rgb)
+
+    x4 = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=1)
+    x4 = torch.cat([x4, torch.rand(256, 1, generator=g) / 3.0], 1)
+    vd = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=1)
+    with torch.no_grad():
+        yb = m.bg_implicit_network(x4, {"frame": scene["frame_code"]})[0]
+        rb = m.bg_rendering_network(None, None, vd, None, yb[:, 1:], scene["frame_code"])
+    save("bg_nets", x=x4, view=vd, out=yb, rgb=rb)
+
+    sdfv = torch.linspace(-0.5, 4.0, 200)
+    save("density", sdf=sdfv, sigma=m.density(sdfv).detach(),
+         sigma_b=m.density(sdfv, beta=torch.tensor(0.013)).detach(), beta=m.density.get_beta().detach())
+
+    # deformer: points around the posed body
+    vp = p0["verts_p"]
+    pts = vp[torch.randint(0, vp.shape[0], (512,), generator=g)] + 0.06 * torch.randn(512, 3, generator=g)
+    xc, outl = m.deformer_list[0].forward(pts, p0["tfs"][None], return_weights=False, inverse=True,
+                                          smpl_verts=vp[None])
+    xd = m.deformer_list[0].forward_skinning(xc[None], None, p0["tfs"][None])[0]
+    save("deformer", pts=pts, x_c=xc, outlier=outl, x_d=xd)
+
+    # ---- sampler + full forward -----------------------------------------------------
+    for name, Sn, R, region in (("forward_S64_R48", 64, 48, "boxes"), ("forward_S16_R96", 16, 96, "image")):
+        sc = S.make_scene(P=2, S=Sn, seed=42)
+        mm = build_ref_model(ref, sc)
+        inputs = S.make_rays(sc, R, seed=1234, region=region)
+        hits = S.make_hit_lists(sc, inputs)
+        o = ref_forward(ref, mm, sc, inputs, hits)
+        flat = {k: v for k, v in o.items() if isinstance(v, torch.Tensor)}
+        for p in range(2):
+            flat[f"z_vals_{p}"] = o["z_vals"][p]
+            flat[f"sdf_{p}"] = o["sdf"][p]
+            flat[f"rgb_{p}"] = o["rgb"][p]
+            flat[f"normals_{p}"] = o["normals"][p]
+            flat[f"hits_{p}"] = hits[p]
+        flat["trips"] = np.array(o["trips"])
+        flat["uv"] = inputs["uv"]
+        save(name, **flat)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""CPU: pin oracle/port.py against the outputs of the UNMODIFIED reference modules
+(tests/golden/*.npz, produced by oracle/gen_golden.py in the build container)."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from multiply_b200 import scene as S
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.fixture(scope="module")
+def scene64():
+    return S.make_scene(P=2, S=64, seed=42)
+
+
+def test_implicit_fg(golden_dir, scene64):
+    g = _g(golden_dir, "implicit_fg")
+    p0 = scene64["persons"][0]
+    with torch.no_grad():
+        y = port.implicit_forward(p0["implicit"], torch.from_numpy(g["x"]), p0["cond"], 6)
+    assert np.abs(y.numpy() - g["out"]).max() < 2e-6
+
+
+def test_implicit_fg_grad(golden_dir, scene64):
+    g = _g(golden_dir, "implicit_fg_grad")
+    p0 = scene64["persons"][0]
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    y = port.implicit_forward(p0["implicit"], x, p0["cond"], 6)
+    gr = torch.autograd.grad(y[:, 0].sum(), x)[0]
+    assert np.abs(gr.numpy() - g["grad"]).max() < 2e-6
+
+
+def test_render_fg(golden_dir, scene64):
+    g = _g(golden_dir, "render_fg")
+    p0 = scene64["persons"][0]
+    with torch.no_grad():
+        rgb = port.rendering_forward(p0["render"], "pose_no_view", torch.from_numpy(g["x"]),
+                                     torch.from_numpy(g["normals"]), None, p0["cond"], torch.from_numpy(g["feat"]))
+    assert np.abs(rgb.numpy() - g["rgb"]).max() < 1e-6
+
+
+def test_bg_nets(golden_dir, scene64):
+    g = _g(golden_dir, "bg_nets")
+    with torch.no_grad():
+        y = port.implicit_forward(scene64["bg_implicit"], torch.from_numpy(g["x"]), scene64["frame_code"], 10,
+                                  weight_norm=False)
+        rgb = port.rendering_forward(scene64["bg_render"], "nerf_frame_encoding", None, None,
+                                     torch.from_numpy(g["view"]), None, y[:, 1:],
+                                     frame_latent_code=scene64["frame_code"], weight_norm=False, multires_view=4)
+    assert np.abs(y.numpy() - g["out"]).max() < 2e-6
+    assert np.abs(rgb.numpy() - g["rgb"]).max() < 1e-6
+
+
+def test_density(golden_dir, scene64):
+    g = _g(golden_dir, "density")
+    beta = port.get_beta(scene64["beta_param"])
+    assert float(beta) == float(g["beta"])
+    s = port.laplace_density(torch.from_numpy(g["sdf"]), beta)
+    assert np.array_equal(s.numpy(), g["sigma"])
+    s = port.laplace_density(torch.from_numpy(g["sdf"]), torch.tensor(0.013))
+    assert np.array_equal(s.numpy(), g["sigma_b"])
+
+
+def test_deformer(golden_dir, scene64):
+    g = _g(golden_dir, "deformer")
+    p0 = scene64["persons"][0]
+    xc, outl = port.deform_inverse(torch.from_numpy(g["pts"]), p0)
+    assert np.array_equal(outl.numpy(), g["outlier"])
+    assert np.abs(xc.numpy() - g["x_c"]).max() < 1e-6
+    w, _ = port.query_skinning_weights(xc[None], p0["verts_c"], p0["weights"][None])
+    xd = port.skinning(xc[None], w, p0["tfs"][None], inverse=False)[0]
+    assert np.abs(xd.numpy() - g["x_d"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name,Sn,R,region", [("forward_S64_R48", 64, 48, "boxes"),
+                                              ("forward_S16_R96", 16, 96, "image")])
+def test_forward(golden_dir, name, Sn, R, region):
+    g = _g(golden_dir, name)
+    sc = S.make_scene(P=2, S=Sn, seed=42)
+    inp = S.make_rays(sc, R, seed=1234, region=region)
+    assert np.array_equal(inp["uv"].numpy(), g["uv"]), "synthetic input drifted from the golden's"
+    hits = S.make_hit_lists(sc, inp)
+    for p in range(2):
+        assert np.array_equal(hits[p].numpy(), g[f"hits_{p}"])
+    st = {}
+    o = port.multiply_forward(sc, inp, hits, stats=st, return_samples=True)
+    assert list(st["trips"]) == list(g["trips"])
+    for k in ("rgb_values", "fg_rgb_values", "normal_values", "acc_map", "acc_person_list"):
+        assert np.abs(o[k].numpy() - g[k]).max() < 1e-5, k
+    for p in range(2):
+        assert np.abs(o["_z_vals"][p].numpy() - g[f"z_vals_{p}"]).max() < 2e-4
+        assert np.abs(o["_sdf"][p].numpy() - g[f"sdf_{p}"]).max() < 1e-4
