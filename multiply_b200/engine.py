@@ -1,0 +1,274 @@
+"""Device-side scene objects on top of the C ABI: packed fields, posed bodies, the fused renderer.
+
+PyTorch is used for device memory and streams only; every computation is a call into
+libmultiply_b200.so (see _lib.py).  No fallback path exists.
+"""
+import ctypes as C
+import math
+import torch
+
+from . import _lib as L
+
+
+def _dev(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def set_engine(name):
+    """'tc' = tcgen05 split-fp16 tensor-core engine (default), 'simt' = fp32 validation engine."""
+    L.check(L.lib().mp_set_engine({"simt": 0, "tc": 1}[name]), "mp_set_engine")
+
+
+def get_engine():
+    return {0: "simt", 1: "tc"}[L.lib().mp_get_engine()]
+
+
+def _stack(sd, n_layers, dev, keep):
+    st = L.LinearStack()
+    st.n_layers = n_layers
+    for l in range(n_layers):
+        if f"lin{l}.weight_v" in sd:
+            v = _dev(sd[f"lin{l}.weight_v"], dev)
+            g = _dev(sd[f"lin{l}.weight_g"], dev)
+            keep += [v, g]
+            st.weight_v[l] = v.data_ptr()
+            st.weight_g[l] = g.data_ptr()
+        else:
+            v = _dev(sd[f"lin{l}.weight"], dev)
+            keep.append(v)
+            st.weight_v[l] = v.data_ptr()
+            st.weight_g[l] = None
+        b = _dev(sd[f"lin{l}.bias"], dev)
+        keep.append(b)
+        st.bias[l] = b.data_ptr()
+        st.out_dim[l], st.in_dim[l] = v.shape
+    return st
+
+
+class Field:
+    """Packed ImplicitNet + RenderingNet pair (mp_field_pack)."""
+
+    def __init__(self, implicit_sd, render_sd, background=False, device="cuda"):
+        lib = L.lib()
+        self.device = torch.device(device)
+        keep = []
+        imp = L.ImplicitDesc()
+        imp.lin = _stack(implicit_sd, 9, self.device, keep)
+        imp.d_in = 4 if background else 3
+        imp.multires = 10 if background else 6
+        imp.cond_dim = 32 if background else 69
+        imp.skip_layer = 4
+        ren = L.RenderDesc()
+        n_ren = len([k for k in render_sd if k.startswith("lin") and k.endswith(".bias") and "pose" not in k])
+        ren.lin = _stack(render_sd, n_ren, self.device, keep)
+        ren.mode = 1 if background else 0
+        ren.multires_view = 4 if background else -1
+        if not background:
+            pw, pb = _dev(render_sd["lin_pose.weight"], self.device), _dev(render_sd["lin_pose.bias"], self.device)
+            keep += [pw, pb]
+            ren.lin_pose_weight, ren.lin_pose_bias = pw.data_ptr(), pb.data_ptr()
+        nbytes = lib.mp_field_pack_bytes()
+        self.storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        L.check(lib.mp_field_pack(C.byref(imp), C.byref(ren), int(background), self.storage.data_ptr(), nbytes,
+                                  C.byref(h), L.stream_ptr()), "mp_field_pack")
+        torch.cuda.current_stream().synchronize()   # raw parameter tensors may be released now
+        self.handle = h
+        self.background = background
+
+    def set_cond(self, cond):
+        c = _dev(cond.reshape(-1), self.device)
+        L.check(L.lib().mp_field_set_cond(self.handle, c.data_ptr(), L.stream_ptr()), "mp_field_set_cond")
+        self._cond = c
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                L.lib().mp_field_free(self.handle)
+        except Exception:
+            pass
+
+    # operator-level entry points ------------------------------------------------------
+    def implicit_forward(self, x, want_feat=True, want_grad=False):
+        lib = L.lib()
+        x = _dev(x, self.device)
+        N = x.shape[0]
+        sdf = torch.empty(N, device=self.device)
+        feat = torch.empty(N, 256, device=self.device) if want_feat else None
+        ws = torch.empty(lib.mp_mlp_workspace_bytes(N), dtype=torch.uint8, device=self.device)
+        if want_grad:
+            grad = torch.empty(N, 3, device=self.device)
+            L.check(lib.mp_implicit_forward_grad(self.handle, x.data_ptr(), N, sdf.data_ptr(), L.ptr(feat),
+                                                 grad.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()),
+                    "mp_implicit_forward_grad")
+            return sdf, feat, grad
+        L.check(lib.mp_implicit_forward(self.handle, x.data_ptr(), N, sdf.data_ptr(), L.ptr(feat), ws.data_ptr(),
+                                        ws.numel(), L.stream_ptr()), "mp_implicit_forward")
+        return sdf, feat
+
+    def render_forward(self, points, normals, feat):
+        lib = L.lib()
+        points, normals, feat = (_dev(t, self.device) for t in (points, normals, feat))
+        N = points.shape[0]
+        rgb = torch.empty(N, 3, device=self.device)
+        ws = torch.empty(lib.mp_mlp_workspace_bytes(N), dtype=torch.uint8, device=self.device)
+        L.check(lib.mp_render_forward(self.handle, points.data_ptr(), normals.data_ptr(), feat.data_ptr(), N,
+                                      rgb.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), "mp_render_forward")
+        return rgb
+
+
+class Body:
+    """Canonical SMPL vertices + skinning weights (SMPLDeformer state) and the per-frame pose."""
+
+    def __init__(self, verts_cano, weights, cano_cell=0.2, device="cuda"):
+        lib = L.lib()
+        self.device = torch.device(device)
+        self.verts_c = _dev(verts_cano, self.device)
+        self.weights = _dev(weights, self.device)
+        V = self.verts_c.shape[0]
+        nbytes = lib.mp_body_bytes(V)
+        self.storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        L.check(lib.mp_body_create(self.verts_c.data_ptr(), self.weights.data_ptr(), V, float(cano_cell),
+                                   self.storage.data_ptr(), nbytes, C.byref(h), L.stream_ptr()), "mp_body_create")
+        self.handle = h
+        self.V = V
+
+    def set_pose(self, verts_posed, tfs):
+        self.verts_p = _dev(verts_posed, self.device)
+        self.tfs = _dev(tfs.reshape(24, 4, 4), self.device)
+        L.check(L.lib().mp_body_set_pose(self.handle, self.verts_p.data_ptr(), self.tfs.data_ptr(), L.stream_ptr()),
+                "mp_body_set_pose")
+
+    def deform_inverse(self, x, exact_far=True):
+        x = _dev(x, self.device)
+        N = x.shape[0]
+        xc = torch.empty(N, 3, device=self.device)
+        out = torch.empty(N, dtype=torch.uint8, device=self.device)
+        L.check(L.lib().mp_deform_inverse(self.handle, x.data_ptr(), N, xc.data_ptr(), out.data_ptr(),
+                                          int(exact_far), L.stream_ptr()), "mp_deform_inverse")
+        return xc, out.bool()
+
+    def forward_jac(self, xc):
+        xc = _dev(xc, self.device)
+        N = xc.shape[0]
+        xd = torch.empty(N, 3, device=self.device)
+        J = torch.empty(N, 9, device=self.device)
+        L.check(L.lib().mp_deform_forward_jac(self.handle, xc.data_ptr(), N, xd.data_ptr(), J.data_ptr(),
+                                              L.stream_ptr()), "mp_deform_forward_jac")
+        return xd, J
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                L.lib().mp_body_free(self.handle)
+        except Exception:
+            pass
+
+
+def sampler_cfg(cfg, beta_param, beta_min=1e-4):
+    c = L.SamplerCfg()
+    c.scene_bounding_sphere = cfg["scene_bounding_sphere"]
+    c.near = cfg.get("near", 0.0)
+    c.N_samples = cfg["N_samples"]
+    c.N_samples_eval = cfg["N_samples_eval"]
+    c.N_samples_extra = cfg["N_samples_extra"]
+    c.eps = cfg["eps"]
+    c.beta_iters = cfg["beta_iters"]
+    c.max_total_iters = cfg["max_total_iters"]
+    c.add_tiny = cfg["add_tiny"]
+    c.beta_param = beta_param
+    c.beta_min = beta_min
+    return c
+
+
+class Renderer:
+    """The fused eval forward (mp_render_rays) over a scene dict as produced by scene.make_scene
+    (or assembled from a checkpoint by model.multiply.Multiply)."""
+
+    def __init__(self, scene, device="cuda"):
+        self.device = torch.device(device)
+        self.cfg = scene["cfg"]
+        self.beta_param = float(scene["beta_param"])
+        self.P = len(scene["persons"])
+        self.fields, self.bodies = [], []
+        for person in scene["persons"]:
+            f = Field(person["implicit"], person["render"], background=False, device=device)
+            f.set_cond(person["cond"])
+            scale = float(person.get("scale", 1.0))
+            b = Body(person["verts_c"], person["weights"], cano_cell=0.1001 / max(scale, 1e-3), device=device)
+            b.set_pose(person["verts_p"], person["tfs"])
+            self.fields.append(f)
+            self.bodies.append(b)
+        self.bg = None
+        if scene.get("bg_implicit") is not None:
+            self.bg = Field(scene["bg_implicit"], scene["bg_render"], background=True, device=device)
+            self.bg.set_cond(scene["frame_code"])
+        self._ws = None
+        self.n = self.cfg["N_samples"] + self.cfg["N_samples_extra"] + 1
+
+    def update_person(self, p, person):
+        """New pose for person p (per-frame update): cond, posed vertices, bone transforms."""
+        self.fields[p].set_cond(person["cond"])
+        self.bodies[p].set_pose(person["verts_p"], person["tfs"])
+
+    def render(self, inputs, hit_lists, debug=False):
+        """inputs: uv [1,R,2], pose [1,4,4], intrinsics [1,4,4] (CUDA or CPU tensors);
+        hit_lists: per person int64 ray ids (empty list -> ray 0, multiply.py:262-263).
+        Returns the eval output dict of Multiply.forward (multiply.py:589-598)."""
+        lib = L.lib()
+        dev = self.device
+        uv = _dev(inputs["uv"].reshape(-1, 2), dev)
+        pose = _dev(inputs["pose"].reshape(4, 4), dev)
+        K = _dev(inputs["intrinsics"].reshape(4, 4), dev)
+        R = uv.shape[0]
+        sc = L.Scene()
+        sc.sampler = sampler_cfg(self.cfg, self.beta_param)
+        sc.P = self.P
+        hits = []
+        for p in range(self.P):
+            h = hit_lists[p]
+            if h.numel() == 0:
+                h = torch.zeros(1, dtype=torch.int64)
+            h = h.to(device=dev, dtype=torch.int64).contiguous()
+            hits.append(h)
+            sc.body[p] = self.bodies[p].handle
+            sc.field[p] = self.fields[p].handle
+            sc.hit_index[p] = h.data_ptr()
+            sc.hit_count[p] = h.numel()
+        sc.bg_field = self.bg.handle if self.bg is not None else None
+        need = lib.mp_render_workspace_bytes(C.byref(sc), R)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out = L.RenderOut()
+        res = {
+            "rgb_values": torch.empty(R, 3, device=dev),
+            "fg_rgb_values": torch.empty(R, 3, device=dev),
+            "normal_values": torch.empty(R, 3, device=dev),
+            "acc_map": torch.empty(R, device=dev),
+            "acc_person_list": torch.empty(R, self.P, device=dev),
+        }
+        for k, v in res.items():
+            setattr(out, k, v.data_ptr())
+        dbg = {}
+        if debug:
+            n = self.n
+            dbg["trips"] = torch.zeros(self.P, dtype=torch.int32, device=dev)
+            dbg["bg_T"] = torch.empty(R, device=dev)
+            out.trips = dbg["trips"].data_ptr()
+            out.bg_T = dbg["bg_T"].data_ptr()
+            for p in range(self.P):
+                Rp = hits[p].numel()
+                dbg[f"z_vals_{p}"] = torch.empty(Rp, n + 1, device=dev)
+                dbg[f"sdf_{p}"] = torch.empty(Rp, n, device=dev)
+                dbg[f"rgb_{p}"] = torch.empty(Rp, n, 3, device=dev)
+                dbg[f"normals_{p}"] = torch.empty(Rp, n, 3, device=dev)
+                out.z_vals[p] = dbg[f"z_vals_{p}"].data_ptr()
+                out.sdf[p] = dbg[f"sdf_{p}"].data_ptr()
+                out.rgb[p] = dbg[f"rgb_{p}"].data_ptr()
+                out.normals[p] = dbg[f"normals_{p}"].data_ptr()
+        L.check(lib.mp_render_rays(C.byref(sc), uv.data_ptr(), pose.data_ptr(), K.data_ptr(), R, C.byref(out),
+                                   self._ws.data_ptr(), self._ws.numel(), L.stream_ptr()), "mp_render_rays")
+        self._keep = (uv, pose, K, hits)
+        res.update(dbg)
+        return res
