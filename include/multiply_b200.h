@@ -94,6 +94,12 @@ int mp_field_set_cond(mp_net_t* f, const float* cond /*[cond_dim]*/, void* strea
 int mp_set_engine(int engine);
 int mp_get_engine(void);
 
+/* Per-launch timing of the tcgen05 MLP kernel (CUDA events on the launching stream), by program kind:
+ * [0] sdf-only, [1] forward (sdf + features), [2] full shade, [3] background.  mp_profile_read synchronises
+ * on the recorded events and returns summed milliseconds, launch counts and processed points (host arrays of 4). */
+int mp_profile_enable(int on);
+int mp_profile_read(double* ms_host, long long* launches_host, double* points_host, int reset);
+
 /* ImplicitNet.forward (networks.py:126-208): x [N,d_in] -> out [N,257] (sdf | feature).
  * sdf / feat may be NULL.  Replaces `self.foreground_implicit_network_list[p](x_c, cond)`. */
 int mp_implicit_forward(mp_net_t* f, const float* x, int N, float* sdf /*[N]*/, float* feat /*[N,256]*/,

@@ -80,6 +80,8 @@ SIGNATURES = {
     "mp_field_set_cond": (_I, [_VP, _VP, _VP]),
     "mp_set_engine": (_I, [_I]),
     "mp_get_engine": (_I, []),
+    "mp_profile_enable": (_I, [_I]),
+    "mp_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double), _I]),
     "mp_implicit_forward": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _SZ, _VP]),
     "mp_implicit_forward_grad": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mp_render_forward": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _SZ, _VP]),

@@ -69,8 +69,7 @@ __global__ void bg_composite_kernel(const float* __restrict__ sdf, const float* 
   float zn = (lane < 31) ? bg_linspace32(30 - lane) * inv_bound : 0.f;
   float dist = (lane < 31) ? (zc - zn) : 1e10f;
   float fe = dist * dens;
-  float incl = warp_scan_incl(fe, lane);
-  float T = expf(-(incl - fe));
+  float T = expf(-warp_scan_excl(fe, lane));
   float wgt = (1.f - expf(-fe)) * T;
   for (int k = 0; k < 3; ++k) {
     float v = warp_sum(wgt * rgb[3 * i + k]);

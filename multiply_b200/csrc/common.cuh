@@ -191,6 +191,13 @@ __device__ __forceinline__ float warp_scan_incl(float v, int lane) {
   return v;
 }
 
+// exclusive warp scan (no "inclusive minus own" cancellation when one lane holds a huge term)
+__device__ __forceinline__ float warp_scan_excl(float v, int lane) {
+  float incl = warp_scan_incl(v, lane);
+  float up = __shfl_up_sync(0xffffffffu, incl, 1);
+  return lane == 0 ? 0.f : up;
+}
+
 // LaplaceDensity.density_func (lib/model/density.py:20-25):
 //   alpha * (0.5 + 0.5 * sign(sdf) * expm1(-|sdf| / beta)),  alpha = 1 / beta
 __device__ __forceinline__ float laplace_density(float sdf, float beta) {

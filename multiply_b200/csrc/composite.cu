@@ -105,7 +105,7 @@ __global__ void composite_kernel(CompositePersons cp, int R, int n, float beta, 
   int b = lane * C, e = min(K, b + C);
   float s1 = 0.f;
   for (int k = b; k < e; ++k) s1 += ssd[k];
-  float run = warp_scan_incl(s1, lane) - s1;
+  float run = warp_scan_excl(s1, lane);
   float last_excl = 0.f;
   for (int k = b; k < e; ++k) {
     float v = ssd[k];

@@ -115,6 +115,8 @@ int mp_field_pack(const mp_implicit_desc_t* imp, const mp_render_desc_t* ren, in
   Arena a(storage, storage_bytes);
   const int E = f.emb_dim;
   int rc = 0;
+  // padded tails of biases / weight tiles must read as zero (0 * garbage could be NaN)
+  MP_CHECK_CUDA(cudaMemsetAsync(storage, 0, mp_field_pack_bytes(), st));
   // ---- implicit net -------------------------------------------------------------------
   float* nat[MP_MAX_LAYERS];
   for (int l = 0; l < f.n_imp && rc == 0; ++l) {
@@ -134,7 +136,7 @@ int mp_field_pack(const mp_implicit_desc_t* imp, const mp_render_desc_t* ren, in
     nat[l] = a.take<float>((size_t)o * in);
     f.imp_W[l] = nat[l];
     f.imp_Wt[l] = a.take<float>((size_t)in * o);
-    f.imp_b[l] = a.take<float>(o);
+    f.imp_b[l] = a.take<float>(o < 264 ? 264 : o);   // padded: the tcgen05 epilogue reads 256 columns
     if (!a.ok) break;
     float scale = (l == f.skip_layer) ? (float)(1.0 / sqrt(2.0)) : 1.0f;
     rc = fold(imp->lin.weight_v[l], imp->lin.weight_g[l], o, in, scale, nat[l], st);
@@ -177,7 +179,7 @@ int mp_field_pack(const mp_implicit_desc_t* imp, const mp_render_desc_t* ren, in
       rnat[l] = a.take<float>((size_t)o * in);
       f.ren_W[l] = rnat[l];
       f.ren_Wt[l] = a.take<float>((size_t)in * o);
-      f.ren_b[l] = a.take<float>(o);
+      f.ren_b[l] = a.take<float>(o < 264 ? 264 : o);
       if (!a.ok) break;
       rc = fold(ren->lin.weight_v[l], ren->lin.weight_g[l], o, in, 1.0f, rnat[l], st);
       if (rc) break;
@@ -197,7 +199,7 @@ int mp_field_pack(const mp_implicit_desc_t* imp, const mp_render_desc_t* ren, in
       g_launches++;
     }
     if (rc == 0 && a.ok) {
-      f.ren_b0_eff = a.take<float>(out0);
+      f.ren_b0_eff = a.take<float>(out0 < 264 ? 264 : out0);
       f.ren_b0_base = a.take<float>(out0);
       f.ren_W0cond = a.take<float>((size_t)f.ren_cond_dim * out0);
       if (a.ok) {

@@ -1,13 +1,986 @@
-// tcgen05 engine (placeholder until the kernel lands): fails loudly.
+// tcgen05 engine: the fused ImplicitNet (+ backward for normals) + RenderingNet chain on the
+// 5th-generation tensor cores of sm_100a.
+//   reference: /root/reference/code/lib/model/networks.py:126-208 (ImplicitNet.forward),
+//              :263-312 (RenderingNet.forward), lib/model/multiply.py:620-661 (forward_gradient)
+//
+// Design:
+//   * one persistent CTA per SM; a tile is 128 sample points (MMA M = 128, cta_group::1).
+//   * every layer is D[128 x 256] (fp32, 256 TMEM columns) = A[128 x K] . W^T, K in chunks of 64.
+//     A (the activations) lives in shared memory as fp16 hi + fp16 lo (K-major, 128B swizzle);
+//     the weights are streamed as pre-swizzled fp16 hi/lo tiles ("slots", 256 x 64, 32 KB) by
+//     the TMA engine (cp.async.bulk + mbarrier complete_tx) through a 3-slot ring.
+//   * split precision: D = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo (three kind::f16 MMAs per K-step,
+//     fp32 accumulate) — 22 significand bits per operand, which is what keeps RGB/SDF within the
+//     1e-4 gate that a single bf16/fp16 pass misses by two orders of magnitude.
+//   * warp roles: warp 0 = weight loader, warp 1 = MMA issuer (one elected lane),
+//     warps 2..9 = epilogue (TMEM -> registers -> activation -> fp16 hi/lo -> shared memory).
+//   * the whole per-sample chain runs inside the tile: embed, L0..L7 (+ sigma' stash), SDF dot,
+//     L8 features, the reverse sweep B7..B0 (d sdf / d x_c), normals, colour layers, RGB.
 #include "common.cuh"
+#include <vector>
+
 namespace mp {
-size_t tc_pack_bytes() { return 0; }
-int tc_pack(Field& f, Arena& a, cudaStream_t st) { f.tc = nullptr; return 0; }
-size_t tc_workspace_bytes(int N) { return 0; }
-int tc_sdf_list(const Field&, const float*, const int*, const int*, int, float*, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 engine not built"); return -9; }
-int tc_shade_list(const Field&, const float*, const int*, const int*, int, const float*, float*, float*, float*,
-                  float*, float*, void*, size_t, cudaStream_t) { set_error("tcgen05 engine not built"); return -9; }
-int tc_bg(const Field&, const float*, const float*, int, float*, float*, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 engine not built"); return -9; }
+
+// ---------------------------------------------------------------------------------------------
+// program description
+// ---------------------------------------------------------------------------------------------
+enum { EPI_SOFTPLUS = 0, EPI_FEAT = 1, EPI_BWD = 2, EPI_RELU = 3 };
+enum {
+  F_SAVE_SIG = 1,      // store d softplus / dz to the sigma' scratch (forward, grad mode)
+  F_INJECT_EMB = 2,    // columns >= inj_col receive the input embedding (skip connection, networks.py:166)
+  F_SDF_DOT = 4,       // sdf = h7 . W8[0,:] + b8[0]
+  F_SEED_BWD = 8,      // after this step: A = W8[0,:] * sigma'_7 (start of the reverse sweep)
+  F_SKIP_GRAD = 16,    // reverse sweep: columns >= inj_col are d/d embed of the skip; park them, zero A there
+  F_FINAL_GRAD = 32,   // reverse sweep end: d sdf / d x -> normal ; then reload the features into A
+  F_EXTRA_IN = 64,     // colour layer 0: add W0[:, :n_extra] . extra inputs
+  F_RGB_OUT = 128,     // last colour layer: rgb = sigmoid(h . Wrgb^T + b)
+  F_FEAT_OUT = 256     // write the fp32 features to feat_out (operator API)
+};
+constexpr int kMaxSteps = 24;
+constexpr int kSlotBytes = 32768;          // 256 rows x 64 fp16
+constexpr int kRing = 3;
+
+struct TcStep {
+  int nk;               // 64-wide K chunks of A consumed by this layer
+  int epi;
+  int flags;
+  int sig;              // sigma' scratch layer (save: forward, load: reverse) or -1
+  const float* bias;    // [256] or nullptr
+  int ncols;            // output columns that carry data (the rest are padding)
+};
+
+struct TcProgram {
+  int nsteps;
+  int slots_per_tile;
+  TcStep step[kMaxSteps];
+  const uint4* blob;     // weight slots in consumption order
+  const float* inv_scale;   // [nsteps] 2^-s of each step's weights
+  // network constants
+  int d_in, multires, E, inj_col, n_extra, col_n;   // col_n: width of the colour hidden layers
+  const float* w8row;    // W8[0,:]  [256]
+  const float* b8;       // b8[0]
+  const float* W0x;      // colour layer 0, extra-input columns, transposed [n_extra][256]
+  const float* Wrgb;     // [3][256]
+  const float* brgb;     // [3]
+};
+
+struct TcIO {
+  const float* x;        // [cap, d_in] canonical points (compact list)
+  const int* slot;       // [cap] output slot of each point or nullptr (identity)
+  const int* count;      // device count or nullptr (= cap)
+  int cap;
+  const float* jinv;     // [cap, 9] or nullptr
+  const float* extra;    // [cap, n_extra] extra colour inputs (background view embedding) or nullptr
+  float* sdf_out;        // scattered by slot
+  float* rgb_out;        // [slots,3]
+  float* nrm_out;        // [slots,3]
+  float* grad_out;       // [cap,3] dense or nullptr
+  float* feat_out;       // [cap,256] dense or nullptr
+  char* scratch;         // per-CTA scratch
+  size_t scratch_per_cta;
+};
+
+// per-CTA scratch layout (bytes)
+constexpr size_t kSigBytes = (size_t)8 * 64 * 128 * 16;      // sigma' [8][64][128] float4
+constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo chunks
+constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
+constexpr size_t kMiscBytes = (size_t)128 * 16 * 4;          // partial sums / normals [128][16]
+constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes;
+
+// shared memory carve-up
+constexpr int kABytes = 2 * 4 * 128 * 128;                   // hi + lo, 4 K-blocks of [128 x 128B]
+constexpr int kSmemBytes = kABytes + kRing * kSlotBytes + 256 + 1024;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major, 1), [32,46) SBO>>4 = 1024B between
+//   8-row groups, [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N = 256, M = 128
+__device__ __forceinline__ uint32_t make_idesc() { return (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24); }
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers
+// ---------------------------------------------------------------------------------------------
+// byte offset of (row, 8-column chunk `ch` of K-block `kb`) in the swizzled A image
+__device__ __forceinline__ uint32_t a_off(int row, int kb, int ch) {
+  return (uint32_t)(kb * 16384 + row * 128 + ((ch ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    float2 f = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+  }
+  hi = make_uint4(*(uint32_t*)&h[0], *(uint32_t*)&h[1], *(uint32_t*)&h[2], *(uint32_t*)&h[3]);
+  lo = make_uint4(*(uint32_t*)&l[0], *(uint32_t*)&l[1], *(uint32_t*)&l[2], *(uint32_t*)&l[3]);
+}
+
+__device__ __forceinline__ void store_a8(char* A, int row, int col, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  uint32_t o = a_off(row, col >> 6, (col >> 3) & 7);
+  *reinterpret_cast<uint4*>(A + o) = hi;
+  *reinterpret_cast<uint4*>(A + 65536 + o) = lo;
+}
+
+// element k of the positional embedding of x (embedders.py:8-34)
+__device__ __forceinline__ float embed_elem(const float* x, int d, int k) {
+  if (k < d) return x[k];
+  int f = (k - d) / (2 * d), r = (k - d) - f * 2 * d;
+  float t = __fmul_rn(x[r < d ? r : r - d], (float)(1 << f));
+  return r < d ? sinf(t) : cosf(t);
+}
+
+__device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// softplus(beta=100, threshold=20) and its derivative (networks.py:85)
+__device__ __forceinline__ void softplus_fast(float z, float& y, float& d) {
+  float t = 100.f * z;
+  if (t > 20.f) {
+    y = z;
+    d = 1.f;
+  } else {
+    float u = __expf(t);
+    y = __logf(1.f + u) * 0.01f;
+    d = __fdividef(u, 1.f + u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
+                                                          const __grid_constant__ TcIO io) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
+  char* base = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  char* A = base;                                   // [hi | lo] x 4 K-blocks
+  char* ring = base + kABytes;                      // kRing weight slots
+  uint64_t* bars = (uint64_t*)(ring + kRing * kSlotBytes);
+  uint64_t* full = bars;                            // [kRing]
+  uint64_t* empty = bars + kRing;                   // [kRing]
+  uint64_t* d_full = bars + 2 * kRing;
+  uint64_t* a_ready = bars + 2 * kRing + 1;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kRing + 2);
+
+  const int count = io.count ? min(io.cap, *io.count) : io.cap;
+  const int ntiles = (count + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(d_full, 1);
+    mbar_init(a_ready, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const char* src = (const char*)P.blob;
+        for (int s = 0; s < P.slots_per_tile; ++s, ++it) {
+          int r = it % kRing;
+          uint32_t ph = (it / kRing) & 1;
+          mbar_wait(&empty[r], ph ^ 1);
+          mbar_expect_tx(&full[r], kSlotBytes);
+          bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)s * kSlotBytes, kSlotBytes, &full[r]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      const uint32_t a_hi = smem_u32(A), a_lo = smem_u32(A) + 65536;
+      uint32_t it = 0, ar_ph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = 0; s < P.nsteps; ++s) {
+          mbar_wait(a_ready, ar_ph);
+          ar_ph ^= 1;
+          tc_fence_after();
+          const int nk = P.step[s].nk;
+          uint32_t acc = 0;
+          for (int kc = 0; kc < nk; ++kc) {
+            // hi slot: A_hi.W_hi + A_lo.W_hi
+            int r = it % kRing;
+            mbar_wait(&full[r], (it / kRing) & 1);
+            tc_fence_after();
+            uint32_t wb = smem_u32(ring + (size_t)r * kSlotBytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              uint64_t bd = make_desc(wb + ks * 32);
+              umma_f16(tmem, make_desc(a_hi + kc * 16384 + ks * 32), bd, idesc, acc);
+              acc = 1;
+              umma_f16(tmem, make_desc(a_lo + kc * 16384 + ks * 32), bd, idesc, 1);
+            }
+            umma_commit(&empty[r]);
+            ++it;
+            // lo slot: A_hi.W_lo
+            r = it % kRing;
+            mbar_wait(&full[r], (it / kRing) & 1);
+            tc_fence_after();
+            wb = smem_u32(ring + (size_t)r * kSlotBytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(tmem, make_desc(a_hi + kc * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+            umma_commit(&empty[r]);
+            ++it;
+          }
+          umma_commit(d_full);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;       // column half: 0 -> cols [0,128), 1 -> [128,256)
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+    char* scr = io.scratch + (size_t)blockIdx.x * io.scratch_per_cta;
+    float4* sig = (float4*)scr;                                  // [8][64][128]
+    uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
+    float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
+    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][16]
+    uint32_t df_ph = 0;
+    const int d = P.d_in, E = P.E;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int pt = tile * 128 + row;
+      const bool valid = pt < count;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid)
+        for (int a = 0; a < d; ++a) x[a] = io.x[(size_t)pt * d + a];
+      const int slot = valid ? (io.slot ? io.slot[pt] : pt) : 0;
+      // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
+      {
+        const int nk0 = P.step[0].nk;
+        const int ncol = nk0 * 64;
+        const int c0 = half * (ncol / 2), c1 = c0 + ncol / 2;
+        for (int c = c0; c < c1; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? embed_elem(x, d, c + j) : 0.f;
+          store_a8(A, row, c, v);
+        }
+        fence_async_smem();
+        mbar_arrive(a_ready);
+      }
+      // colour-net extra inputs: foreground [x_c, n] (networks.py:281), background view-dir embedding (:275)
+      float xin[27];
+#pragma unroll
+      for (int e = 0; e < 27; ++e) xin[e] = 0.f;
+      if (io.extra) {
+        float dv[3] = {0.f, 0.f, 0.f};
+        if (valid)
+          for (int a = 0; a < 3; ++a) dv[a] = io.extra[(size_t)pt * 3 + a];
+#pragma unroll
+        for (int e = 0; e < 27; ++e) xin[e] = embed_elem(dv, 3, e);
+      } else {
+        xin[0] = x[0];
+        xin[1] = x[1];
+        xin[2] = x[2];
+      }
+      for (int s = 0; s < P.nsteps; ++s) {
+        const TcStep st = P.step[s];
+        const float isc = P.inv_scale[s];
+        mbar_wait(d_full, df_ph);
+        df_ph ^= 1;
+        tc_fence_after();
+        if (st.flags & F_FINAL_GRAD) ep_bar();           // skip-gradient parked by the other column half
+        float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
+        const int cbeg = half * 128, cend = cbeg + 128;
+        for (int c = cbeg; c < cend; c += 32) {
+          float v[32];
+          tmem_ld32(t_row + (uint32_t)c, v);
+          if (st.epi == EPI_SOFTPLUS) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+              float4 b4 = __ldg((const float4*)(st.bias + c + 4 * g4));
+              float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              float dd[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float z = fmaf(v[4 * g4 + j], isc, bb[j]);
+                softplus_fast(z, v[4 * g4 + j], dd[j]);
+              }
+              if (st.flags & F_SAVE_SIG)
+                sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+            }
+            if (st.flags & F_INJECT_EMB) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + j >= P.inj_col) v[j] = embed_elem(x, d, c + j - P.inj_col);
+            }
+            if (st.flags & F_SDF_DOT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dot0 = fmaf(v[j], __ldg(P.w8row + c + j), dot0);
+            }
+          } else if (st.epi == EPI_FEAT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], isc, __ldg(st.bias + c + j));
+            if ((st.flags & F_FEAT_OUT) && io.feat_out && valid) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else if (st.epi == EPI_BWD) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+              int col = c + 4 * g4;
+              if ((st.flags & F_FINAL_GRAD)) {
+                // d / d embed of layer 0 : plain scaled accumulator (first E columns matter)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * g4 + j] *= isc;
+              } else if ((st.flags & F_SKIP_GRAD) && col + 3 >= P.inj_col) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  int cc = col + j;
+                  float gval = v[4 * g4 + j] * isc;
+                  if (cc >= P.inj_col) {
+                    ge[(size_t)(cc - P.inj_col) * 128 + row] = gval;
+                    v[4 * g4 + j] = 0.f;
+                  } else {
+                    float4 s4 = sig[((size_t)st.sig * 64 + (col >> 2)) * 128 + row];
+                    float sg = j == 0 ? s4.x : (j == 1 ? s4.y : (j == 2 ? s4.z : s4.w));
+                    v[4 * g4 + j] = gval * sg;
+                  }
+                }
+              } else {
+                float4 s4 = sig[((size_t)st.sig * 64 + (col >> 2)) * 128 + row];
+                v[4 * g4 + 0] = v[4 * g4 + 0] * isc * s4.x;
+                v[4 * g4 + 1] = v[4 * g4 + 1] * isc * s4.y;
+                v[4 * g4 + 2] = v[4 * g4 + 2] * isc * s4.z;
+                v[4 * g4 + 3] = v[4 * g4 + 3] * isc * s4.w;
+              }
+            }
+            if (st.flags & F_FINAL_GRAD) {
+              // park d/d embed (layer-0 part) next to the skip part: ge[E + k]... combined below
+              if (c < 128) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j];
+              }
+            }
+          } else {   // EPI_RELU
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], isc, __ldg(st.bias + c + j));
+            if (st.flags & F_EXTRA_IN) {
+#pragma unroll
+              for (int e = 0; e < 27; ++e) {
+                if (e < P.n_extra) {
+                  const float xe = xin[e];
+                  const float4* w4 = (const float4*)(P.W0x + e * 256 + c);
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 ww = __ldg(w4 + j4);
+                    v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
+                    v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
+                    v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
+                    v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (st.flags & F_RGB_OUT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                dot0 = fmaf(v[j], __ldg(P.Wrgb + c + j), dot0);
+                dot1 = fmaf(v[j], __ldg(P.Wrgb + 256 + c + j), dot1);
+                dot2 = fmaf(v[j], __ldg(P.Wrgb + 512 + c + j), dot2);
+              }
+            }
+          }
+          // activations of this chunk -> A (fp16 hi/lo, swizzled) unless this is the last layer
+          if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) store_a8(A, row, c + j, v + j);
+            if (st.epi == EPI_FEAT && (s + 1 < P.nsteps)) {
+              // stash the feature chunks (they come back as the colour net's input)
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 hi, lo;
+                split8(v + j, hi, lo);
+                int chunk = (c + j) >> 3;
+                fsc[(size_t)chunk * 128 + row] = hi;
+                fsc[(size_t)(32 + chunk) * 128 + row] = lo;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        // ---- step-specific tails ----
+        if (st.flags & F_SDF_DOT) {
+          misc[row * 16 + half] = dot0;
+          __threadfence_block();
+          ep_bar();
+          if (half == 0 && valid && io.sdf_out) io.sdf_out[slot] = misc[row * 16] + misc[row * 16 + 1] + __ldg(P.b8);
+          ep_bar();
+        }
+        if (st.flags & F_SEED_BWD) {
+          // A = W8[0,:] * sigma'_7    (d sdf / d z7)
+          for (int c = cbeg; c < cend; c += 8) {
+            float4 s0 = sig[((size_t)7 * 64 + (c >> 2)) * 128 + row];
+            float4 s1 = sig[((size_t)7 * 64 + (c >> 2) + 1) * 128 + row];
+            float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= __ldg(P.w8row + c + j);
+            store_a8(A, row, c, v);
+          }
+        }
+        if (st.flags & F_SKIP_GRAD) {
+          __threadfence_block();
+        }
+        if (st.flags & F_FINAL_GRAD) {
+          __threadfence_block();
+          ep_bar();
+          if (half == 0) {
+            // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos)
+            float g[3] = {0.f, 0.f, 0.f};
+            for (int a = 0; a < d && a < 3; ++a) {
+              float acc = ge[(size_t)a * 128 + row];
+              for (int f = 0; f < P.multires; ++f) {
+                float fr = (float)(1 << f);
+                float t = __fmul_rn(x[a], fr);
+                float sn, cs;
+                sincosf(t, &sn, &cs);
+                float gs = ge[(size_t)(d + 2 * f * d + a) * 128 + row];
+                float gc = ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row];
+                acc += fr * (cs * gs - sn * gc);
+              }
+              g[a] = acc;
+            }
+            if (io.grad_out && valid) {
+              io.grad_out[3 * (size_t)pt] = g[0];
+              io.grad_out[3 * (size_t)pt + 1] = g[1];
+              io.grad_out[3 * (size_t)pt + 2] = g[2];
+            }
+            float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+            if (io.jinv && valid) {
+              const float* J = io.jinv + 9 * (size_t)pt;
+              float v0 = g[0] * J[0] + g[1] * J[3] + g[2] * J[6];
+              float v1 = g[0] * J[1] + g[1] * J[4] + g[2] * J[7];
+              float v2 = g[0] * J[2] + g[1] * J[5] + g[2] * J[8];
+              float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
+              v0 /= nr; v1 /= nr; v2 /= nr;
+              float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
+              n0 = v0 / n2r; n1 = v1 / n2r; n2 = v2 / n2r;
+              if (io.nrm_out) {
+                io.nrm_out[3 * (size_t)slot] = n0;
+                io.nrm_out[3 * (size_t)slot + 1] = n1;
+                io.nrm_out[3 * (size_t)slot + 2] = n2;
+              }
+            }
+            misc[row * 16 + 4] = n0;
+            misc[row * 16 + 5] = n1;
+            misc[row * 16 + 6] = n2;
+          }
+          __threadfence_block();
+          ep_bar();
+          xin[3] = misc[row * 16 + 4];
+          xin[4] = misc[row * 16 + 5];
+          xin[5] = misc[row * 16 + 6];
+          // features back into A for the colour net
+          if (s + 1 < P.nsteps) {
+            for (int c = cbeg; c < cend; c += 8) {
+              int chunk = c >> 3;
+              uint32_t o = a_off(row, c >> 6, chunk & 7);
+              *reinterpret_cast<uint4*>(A + o) = fsc[(size_t)chunk * 128 + row];
+              *reinterpret_cast<uint4*>(A + 65536 + o) = fsc[(size_t)(32 + chunk) * 128 + row];
+            }
+          }
+        }
+        if (st.flags & F_RGB_OUT) {
+          misc[row * 16 + 8 + half * 4 + 0] = dot0;
+          misc[row * 16 + 8 + half * 4 + 1] = dot1;
+          misc[row * 16 + 8 + half * 4 + 2] = dot2;
+          __threadfence_block();
+          ep_bar();
+          if (half == 0 && valid && io.rgb_out) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float z = misc[row * 16 + 8 + k] + misc[row * 16 + 12 + k] + __ldg(P.brgb + k);
+              io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
+            }
+          }
+          ep_bar();
+        }
+        // hand A (and the drained accumulator) to the MMA warp for the next step of this tile;
+        // the last step's hand-over is the next tile's prologue arrival
+        if (s + 1 < P.nsteps) {
+          fence_async_smem();
+          mbar_arrive(a_ready);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------
+struct TcBlob {
+  TcProgram sdf_prog;     // L0..L7 + sdf dot
+  TcProgram full_prog;    // forward + reverse + colour
+  TcProgram fwd_prog;     // L0..L8 (sdf + features), operator API
+  bool has_full;
+};
+
+__global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restrict__ out) {
+  __shared__ float s[256];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+  s[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] = fmaxf(s[threadIdx.x], s[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // scale = 2^s with max|W| * 2^s in (2^13, 2^14]  (fp16 hi/lo both stay in the normal range)
+    float mx = s[0];
+    int ex = 0;
+    if (mx > 0.f) frexpf(mx, &ex);       // mx = f * 2^ex, f in [0.5,1)
+    float sc = ldexpf(1.f, 14 - ex);
+    out[0] = sc;
+    out[1] = 1.f / sc;
+  }
+}
+
+// One weight slot: B[n][k] for n < 256, k < 64 at K offset kc*64; value from W (natural [out][in], ld):
+//   transposed == 0 : B[n][k] = W[(n_off + n) * ld + k_off + kc*64 + k]   (n < n_valid, kk < k_valid)
+//   transposed == 1 : B[n][k] = W[(k_off + kc*64 + k) * ld + n_off + n]
+__global__ void pack_slot_kernel(const float* __restrict__ W, int ld, int transposed, int n_off, int k_off,
+                                 int n_valid, int k_valid, int kc, const float* __restrict__ scale,
+                                 uint8_t* __restrict__ dst_hi, uint8_t* __restrict__ dst_lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 256 * 64) return;
+  int n = idx >> 6, k = idx & 63;
+  int kk = kc * 64 + k;
+  float w = 0.f;
+  if (n < n_valid && kk < k_valid)
+    w = transposed ? W[(size_t)(k_off + kk) * ld + n_off + n] : W[(size_t)(n_off + n) * ld + k_off + kk];
+  w *= scale[0];
+  __half h = __float2half_rn(w);
+  __half l = __float2half_rn(w - __half2float(h));
+  uint32_t off = (uint32_t)(n * 128 + ((((k >> 3) ^ (n & 7))) << 4) + (k & 7) * 2);
+  *(__half*)(dst_hi + off) = h;
+  *(__half*)(dst_lo + off) = l;
+}
+
+__global__ void copy_strided_kernel(const float* __restrict__ src, int stride, int n, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(size_t)i * stride];
+}
+
+// dst[r][c] (ld 256, zero padded) = src[r * lds + c] for c < ncols
+__global__ void pad_rows_kernel(const float* __restrict__ src, int lds, int nrows, int ncols, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * 256) return;
+  int r = i >> 8, c = i & 255;
+  dst[i] = (c < ncols) ? src[(size_t)r * lds + c] : 0.f;
+}
+
+size_t tc_pack_bytes() {
+  // sdf (58) + fwd (66) + full (162) slots ... share: full program contains fwd which contains sdf
+  return (size_t)170 * kSlotBytes + (1 << 16);
+}
+
+struct PackCtx {
+  Arena* a;
+  cudaStream_t st;
+  uint8_t* blob;
+  int nslots;
+  float* scales;      // [kMaxSteps][2] (scale, inv)
+  float* inv_scale;   // [kMaxSteps]
+  int rc;
+};
+
+static void pack_layer(PackCtx& c, int step, const float* W, int ld, int transposed, int n_off, int k_off,
+                       int n_valid, int k_valid, int nk, int total_elems) {
+  if (c.rc) return;
+  absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step);
+  g_launches++;
+  for (int kc = 0; kc < nk; ++kc) {
+    uint8_t* hi = c.blob + (size_t)c.nslots * kSlotBytes;
+    uint8_t* lo = hi + kSlotBytes;
+    pack_slot_kernel<<<64, 256, 0, c.st>>>(W, ld, transposed, n_off, k_off, n_valid, k_valid, kc,
+                                           c.scales + 2 * step, hi, lo);
+    g_launches++;
+    c.nslots += 2;
+  }
+  copy_strided_kernel<<<1, 1, 0, c.st>>>(c.scales + 2 * step + 1, 1, 1, c.inv_scale + step);
+  g_launches++;
+}
+
+int tc_pack(Field& f, Arena& a, cudaStream_t st) {
+  TcBlob* tb = new TcBlob();
+  memset(tb, 0, sizeof(*tb));
+  f.tc = tb;
+  const int E = f.emb_dim;
+  PackCtx c;
+  c.a = &a;
+  c.st = st;
+  c.rc = 0;
+  c.nslots = 0;
+  c.blob = (uint8_t*)a.take<uint4>((size_t)170 * kSlotBytes / 16);
+  c.scales = a.take<float>(2 * kMaxSteps);
+  c.inv_scale = a.take<float>(kMaxSteps);
+  float* w8row = a.take<float>(256);
+  float* W0x = a.take<float>(32 * 256);
+  float* Wrgb = a.take<float>(3 * 256);
+  MP_REQUIRE(a.ok, "tc_pack: storage too small");
+  MP_CHECK_CUDA(cudaMemsetAsync(c.blob, 0, (size_t)170 * kSlotBytes, st));
+  TcProgram P;
+  memset(&P, 0, sizeof(P));
+  P.blob = (const uint4*)c.blob;
+  P.inv_scale = c.inv_scale;
+  P.d_in = f.d_in;
+  P.multires = f.multires;
+  P.E = E;
+  P.inj_col = kHidden - E;
+  P.w8row = w8row;
+  P.b8 = f.imp_b[8];
+  P.W0x = W0x;
+  P.Wrgb = Wrgb;
+  P.n_extra = f.ren_extra;
+  copy_strided_kernel<<<1, 256, 0, st>>>(f.imp_W[8], 1, 256, w8row);     // W8[0,:]
+  g_launches++;
+  int s = 0;
+  const int nk0 = (E + 63) / 64;
+  // ---- forward L0..L7 ----
+  for (int l = 0; l < 8; ++l) {
+    int in = f.imp_in[l], out = f.imp_out[l];
+    int nk = (l == 0) ? nk0 : 4;
+    pack_layer(c, s, f.imp_W[l], in, 0, 0, 0, out, (l == 0) ? E : in, nk, out * in);
+    P.step[s].nk = nk;
+    P.step[s].epi = EPI_SOFTPLUS;
+    P.step[s].flags = F_SAVE_SIG | ((l == f.skip_layer - 1) ? F_INJECT_EMB : 0) | ((l == 7) ? F_SDF_DOT : 0);
+    P.step[s].sig = l;
+    P.step[s].bias = (l == 0) ? f.imp_b0_eff : f.imp_b[l];
+    P.step[s].ncols = out;
+    ++s;
+  }
+  // sdf-only program: the first 8 steps, no sigma' stash
+  tb->sdf_prog = P;
+  tb->sdf_prog.nsteps = 8;
+  tb->sdf_prog.slots_per_tile = c.nslots;
+  for (int i = 0; i < 8; ++i) tb->sdf_prog.step[i].flags &= ~F_SAVE_SIG;
+  // ---- L8 features ----
+  pack_layer(c, s, f.imp_W[8], 256, 0, 1, 0, 256, 256, 4, 257 * 256);
+  P.step[s].nk = 4;
+  P.step[s].epi = EPI_FEAT;
+  P.step[s].flags = F_FEAT_OUT;
+  P.step[s].sig = -1;
+  P.step[s].bias = f.imp_b[8] + 1;
+  P.step[s].ncols = 256;
+  ++s;
+  tb->fwd_prog = P;
+  tb->fwd_prog.nsteps = 9;
+  tb->fwd_prog.slots_per_tile = c.nslots;
+  for (int i = 0; i < 8; ++i) tb->fwd_prog.step[i].flags &= ~F_SAVE_SIG;
+  const bool fg_chain = (f.ren_mode == 0) && (f.n_ren == 5) && f.ren_out[0] == 256;
+  const bool bg_chain = (f.ren_mode == 1) && (f.n_ren == 2) && f.ren_out[0] <= 256 && f.ren_extra <= 27;
+  tb->has_full = fg_chain || bg_chain;
+  if (bg_chain) {
+    // background: colour layer 0 (view embedding + features -> 128, ReLU) and the rgb head (multiply.py:531)
+    const int in0 = f.ren_extra + 32 + 256, o0 = f.ren_out[0];
+    pack_layer(c, s, f.ren_W[0], in0, 0, 0, f.ren_extra + 32, o0, 256, 4, o0 * in0);
+    P.step[s].nk = 4;
+    P.step[s].epi = EPI_RELU;
+    P.step[s].flags = F_EXTRA_IN | F_RGB_OUT;
+    P.step[s].sig = -1;
+    P.step[s].bias = f.ren_b0_eff;
+    P.step[s].ncols = o0;
+    ++s;
+    pad_rows_kernel<<<div_up(f.ren_extra * 256, 256), 256, 0, st>>>(f.ren_Wt[0], o0, f.ren_extra, o0, W0x);
+    g_launches++;
+    pad_rows_kernel<<<div_up(3 * 256, 256), 256, 0, st>>>(f.ren_W[1], o0, 3, o0, Wrgb);
+    g_launches++;
+    P.brgb = f.ren_b[1];
+    P.nsteps = s;
+    P.slots_per_tile = c.nslots;
+    tb->full_prog = P;
+  }
+  if (fg_chain) {
+    P.step[s - 1].flags |= F_SEED_BWD;
+    // ---- reverse sweep B7..B1: g_{l-1} = (g_l * sigma'_l) . W_l ----
+    for (int l = 7; l >= 1; --l) {
+      int in = f.imp_in[l], out = f.imp_out[l];
+      // B[n][k] = W_l[k][n] : n over in (valid in), k over out (valid out)
+      pack_layer(c, s, f.imp_W[l], in, 1, 0, 0, in, out, 4, out * in);
+      P.step[s].nk = 4;
+      P.step[s].epi = EPI_BWD;
+      P.step[s].flags = (l == f.skip_layer) ? F_SKIP_GRAD : 0;
+      P.step[s].sig = l - 1;
+      P.step[s].bias = nullptr;
+      P.step[s].ncols = in;
+      ++s;
+    }
+    // ---- B0: d/d embed = (g_0 * sigma'_0) . W0[:, :E] ----
+    pack_layer(c, s, f.imp_W[0], f.imp_in[0], 1, 0, 0, E, 256, 4, 256 * f.imp_in[0]);
+    P.step[s].nk = 4;
+    P.step[s].epi = EPI_BWD;
+    P.step[s].flags = F_FINAL_GRAD;
+    P.step[s].sig = -1;
+    P.step[s].bias = nullptr;
+    P.step[s].ncols = E;
+    ++s;
+    // ---- colour net ----
+    for (int l = 0; l < 4; ++l) {
+      int in = (l == 0) ? (6 + 8 + 256) : 256;
+      pack_layer(c, s, f.ren_W[l], in, 0, 0, (l == 0) ? 14 : 0, 256, 256, 4, 256 * in);
+      P.step[s].nk = 4;
+      P.step[s].epi = EPI_RELU;
+      P.step[s].flags = ((l == 0) ? F_EXTRA_IN : 0) | ((l == 3) ? F_RGB_OUT : 0);
+      P.step[s].sig = -1;
+      P.step[s].bias = (l == 0) ? f.ren_b0_eff : f.ren_b[l];
+      P.step[s].ncols = 256;
+      ++s;
+    }
+    // extra-input columns of colour layer 0 (x_c, n), transposed [6][256]; rgb head [3][256]
+    MP_CHECK_CUDA(cudaMemcpyAsync(W0x, f.ren_Wt[0], (size_t)6 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    MP_CHECK_CUDA(cudaMemcpyAsync(Wrgb, f.ren_W[4], (size_t)3 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    P.brgb = f.ren_b[4];
+    P.nsteps = s;
+    P.slots_per_tile = c.nslots;
+    tb->full_prog = P;
+  }
+  MP_REQUIRE(c.nslots <= 170, "tc_pack: slot budget exceeded (%d)", c.nslots);
+  return c.rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+size_t tc_workspace_bytes(int N) { return (size_t)sm_count() * kScratchPerCta + 4096; }
+
+// optional per-launch timing of the tcgen05 kernel (bench.py roofline): CUDA events on the
+// launching stream + an async copy of the device-side point count into pinned memory
+struct ProfEntry {
+  cudaEvent_t e0, e1;
+  int kind;        // 0 sdf-only, 1 forward (sdf+features), 2 full shade, 3 background
+  int cap;
+  int* host_count; // pinned
+};
+static bool g_prof_on = false;
+static std::vector<ProfEntry>* g_prof = nullptr;
+static int* g_prof_pinned = nullptr;
+static int g_prof_used = 0;
+constexpr int kProfMax = 1 << 16;
+
+int prof_enable(int on) {
+  if (on && !g_prof) {
+    g_prof = new std::vector<ProfEntry>();
+    MP_CHECK_CUDA(cudaMallocHost(&g_prof_pinned, kProfMax * sizeof(int)));
+  }
+  g_prof_on = on != 0;
+  return 0;
+}
+int prof_read(double* ms, long long* launches, double* points, int reset) {
+  for (int k = 0; k < 4; ++k) {
+    ms[k] = 0;
+    launches[k] = 0;
+    points[k] = 0;
+  }
+  if (!g_prof) return 0;
+  for (auto& e : *g_prof) {
+    MP_CHECK_CUDA(cudaEventSynchronize(e.e1));
+    float t = 0.f;
+    MP_CHECK_CUDA(cudaEventElapsedTime(&t, e.e0, e.e1));
+    ms[e.kind] += t;
+    launches[e.kind] += 1;
+    int n = e.host_count ? *e.host_count : e.cap;
+    points[e.kind] += (double)(n < e.cap ? n : e.cap);
+  }
+  if (reset) {
+    for (auto& e : *g_prof) {
+      cudaEventDestroy(e.e0);
+      cudaEventDestroy(e.e1);
+    }
+    g_prof->clear();
+    g_prof_used = 0;
+  }
+  return 0;
+}
+
+static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cudaStream_t st, int kind) {
+  int grid = sm_count();
+  int maxtiles = (io.cap + 127) / 128;
+  if (grid > maxtiles) grid = maxtiles;
+  if (grid < 1) return 0;
+  MP_REQUIRE(ws && ws_bytes >= (size_t)grid * kScratchPerCta, "tcgen05 engine: workspace too small (%zu < %zu)",
+             ws_bytes, (size_t)grid * kScratchPerCta);
+  io.scratch = (char*)ws;
+  io.scratch_per_cta = kScratchPerCta;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  ProfEntry pe;
+  const bool prof = g_prof_on && g_prof && g_prof_used < kProfMax;
+  if (prof) {
+    MP_CHECK_CUDA(cudaEventCreate(&pe.e0));
+    MP_CHECK_CUDA(cudaEventCreate(&pe.e1));
+    pe.kind = kind;
+    pe.cap = io.cap;
+    pe.host_count = nullptr;
+    if (io.count) {
+      pe.host_count = g_prof_pinned + g_prof_used++;
+      MP_CHECK_CUDA(cudaMemcpyAsync(pe.host_count, io.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    MP_CHECK_CUDA(cudaEventRecord(pe.e0, st));
+  }
+  tc_chain_kernel<<<grid, 320, kSmemBytes, st>>>(P, io);
+  MP_LAUNCH_CHECK();
+  if (prof) {
+    MP_CHECK_CUDA(cudaEventRecord(pe.e1, st));
+    g_prof->push_back(pe);
+  }
+  return 0;
+}
+
+int tc_sdf_list(const Field& f, const float* xc_list, const int* slot_list, const int* count_dev, int cap,
+                float* sdf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MP_REQUIRE(f.tc, "tcgen05 engine: field not packed");
+  TcBlob* tb = (TcBlob*)f.tc;
+  TcIO io;
+  memset(&io, 0, sizeof(io));
+  io.x = xc_list;
+  io.slot = slot_list;
+  io.count = count_dev;
+  io.cap = cap;
+  io.sdf_out = sdf_out;
+  return tc_launch(tb->sdf_prog, io, ws, ws_bytes, st, 0);
+}
+
+int tc_shade_list(const Field& f, const float* xc_list, const int* slot_list, const int* count_dev, int cap,
+                  const float* Jinv_list, float* sdf_out, float* rgb_out, float* normal_out, float* grad_out,
+                  float* feat_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MP_REQUIRE(f.tc, "tcgen05 engine: field not packed");
+  TcBlob* tb = (TcBlob*)f.tc;
+  TcIO io;
+  memset(&io, 0, sizeof(io));
+  io.x = xc_list;
+  io.slot = slot_list;
+  io.count = count_dev;
+  io.cap = cap;
+  io.jinv = Jinv_list;
+  io.sdf_out = sdf_out;
+  io.rgb_out = rgb_out;
+  io.nrm_out = normal_out;
+  io.grad_out = grad_out;
+  io.feat_out = feat_out;
+  if (!Jinv_list && !grad_out) return tc_launch(tb->fwd_prog, io, ws, ws_bytes, st, 1);
+  MP_REQUIRE(tb->has_full, "tcgen05 engine: this field has no fused shading program");
+  return tc_launch(tb->full_prog, io, ws, ws_bytes, st, 2);
+}
+
+int tc_bg(const Field& f, const float* pts, const float* dirs, int N, float* sdf, float* rgb, void* ws,
+          size_t ws_bytes, cudaStream_t st) {
+  MP_REQUIRE(f.tc, "tcgen05 engine: field not packed");
+  TcBlob* tb = (TcBlob*)f.tc;
+  MP_REQUIRE(tb->has_full && f.ren_mode == 1, "tcgen05 engine: not a background field");
+  TcIO io;
+  memset(&io, 0, sizeof(io));
+  io.x = pts;
+  io.cap = N;
+  io.extra = dirs;
+  io.sdf_out = sdf;
+  io.rgb_out = rgb;
+  return tc_launch(tb->full_prog, io, ws, ws_bytes, st, 3);
+}
+
+}  // namespace mp

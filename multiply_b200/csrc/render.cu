@@ -17,6 +17,8 @@ int tc_shade_list(const Field& f, const float* xc_list, const int* slot_list, co
 int tc_bg(const Field& f, const float* pts, const float* dirs, int N, float* sdf, float* rgb, void* ws,
           size_t ws_bytes, cudaStream_t st);
 size_t tc_workspace_bytes(int N);
+int prof_enable(int on);
+int prof_read(double* ms, long long* launches, double* points, int reset);
 
 // sampler.cu / composite.cu / background.cu
 int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field, const float* dirs,
@@ -154,6 +156,12 @@ int mp_set_engine(int engine) {
   return 0;
 }
 int mp_get_engine(void) { return mp::g_engine; }
+
+int mp_profile_enable(int on) { return mp::prof_enable(on); }
+int mp_profile_read(double* ms_host, long long* launches_host, double* points_host, int reset) {
+  MP_REQUIRE(ms_host && launches_host && points_host, "mp_profile_read: null argument");
+  return mp::prof_read(ms_host, launches_host, points_host, reset);
+}
 
 size_t mp_mlp_workspace_bytes(int N) { return mp::engine_ws_bytes(N) + (size_t)N * (9 + 1) * sizeof(float) + 4096; }
 

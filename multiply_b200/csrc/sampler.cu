@@ -128,8 +128,8 @@ __device__ float error_bound_warp(const float* sz, const float* ss, const float*
     s1 += dist * dens;
     s2 += (expf(-sd[i] / beta) * (dist * dist)) / fb2;
   }
-  float run1 = warp_scan_incl(s1, lane) - s1;
-  float run2 = warp_scan_incl(s2, lane) - s2;
+  float run1 = warp_scan_excl(s1, lane);
+  float run2 = warp_scan_excl(s2, lane);
   float mx = -INFINITY;
   bool has_nan = false;
   for (int i = b; i < e; ++i) {
@@ -242,14 +242,14 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
   for (int i = b; i < e; ++i) {
     float dist = (i < M - 1) ? (sz[i + 1] - sz[i]) : 1e10f;
     float dens = laplace_density(ss[i], beta);
-    s1 += dist * dens;
+    if (i < M - 1) s1 += dist * dens;      // the 1e10 tail interval follows every prefix that is used
     if (cont && i < M - 1) {
       float ds = dstar_interval(sz[i], sz[i + 1], ss[i], ss[i + 1]);
       s2 += (expf(-ds / beta) * (dist * dist)) / fb2;
     }
   }
-  float run1 = warp_scan_incl(s1, lane) - s1;
-  float run2 = warp_scan_incl(s2, lane) - s2;
+  float run1 = warp_scan_excl(s1, lane);
+  float run2 = warp_scan_excl(s2, lane);
   float psum = 0.f;
   for (int i = b; i < e; ++i) {
     float dist = (i < M - 1) ? (sz[i + 1] - sz[i]) : 1e10f;
@@ -285,7 +285,7 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
     sp[i] = p;
     cs += p;
   }
-  float crun = warp_scan_incl(cs, lane) - cs;
+  float crun = warp_scan_excl(cs, lane);
   for (int i = b2; i < e2; ++i) {
     crun += sp[i];
     sc[i + 1] = crun;
