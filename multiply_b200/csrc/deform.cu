@@ -136,6 +136,19 @@ __device__ __forceinline__ void nn_consider(const float4 v, float px, float py, 
 // Returns the nearest vertex index and squared distance.  `found_exact` is true when the grid
 // neighbourhood proves the result is the global arg-min (best distance <= h); otherwise the
 // caller may request a full scan.
+__device__ __forceinline__ void scan_block(const GridHeader& g, const int* __restrict__ cell_start,
+                                           const float4* __restrict__ sorted, int cx, int cy, int cz, int R, float px,
+                                           float py, float pz, float& best, int& bi) {
+  int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
+  if (x0 > x1) return;
+  for (int z = max(cz - R, 0); z <= min(cz + R, g.dim[2] - 1); ++z)
+    for (int y = max(cy - R, 0); y <= min(cy + R, g.dim[1] - 1); ++y) {
+      int base = (z * g.dim[1] + y) * g.dim[0];
+      int b = cell_start[base + x0], e = cell_start[base + x1 + 1];
+      for (int j = b; j < e; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
+    }
+}
+
 __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* __restrict__ cell_start,
                                                const float4* __restrict__ sorted, int V, float px, float py,
                                                float pz, bool full_scan_if_unsure, float& best, int& bi) {
@@ -147,24 +160,24 @@ __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* _
   fy = fminf(fmaxf(fy, -4.f), (float)g.dim[1] + 4.f);
   fz = fminf(fmaxf(fz, -4.f), (float)g.dim[2] + 4.f);
   int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
-  int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-  if (x0 <= x1) {
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z)
-      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-        int base = (z * g.dim[1] + y) * g.dim[0];
-        int b = cell_start[base + x0], e = cell_start[base + x1 + 1];
-        for (int j = b; j < e; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
-      }
-  }
-  // Everything outside the 3x3x3 block is farther than h from the query (when the query's own
-  // cell lies inside the grid), so best <= h^2 proves global optimality.
+  scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
+  // Everything outside the (2R+1)^3 block is farther than R*h from the query (when the query's own
+  // cell lies inside the grid), so best <= (R*h)^2 proves global optimality.
   bool inside = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.dim[0] && cy < g.dim[1] && cz < g.dim[2];
   float hh = g.h * 0.999f;
   bool proven = inside && best <= hh * hh;
   if (!proven && full_scan_if_unsure) {
-    best = INFINITY;
-    bi = 0x7fffffff;
-    for (int j = 0; j < V; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
+    if (inside) {
+      best = INFINITY;
+      bi = 0x7fffffff;
+      scan_block(g, cell_start, sorted, cx, cy, cz, 2, px, py, pz, best, bi);
+      proven = best <= 4.f * hh * hh;
+    }
+    if (!proven) {
+      best = INFINITY;
+      bi = 0x7fffffff;
+      for (int j = 0; j < V; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
+    }
   }
 }
 

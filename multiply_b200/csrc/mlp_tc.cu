@@ -206,16 +206,22 @@ __device__ __forceinline__ float embed_elem(const float* x, int d, int k) {
 __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // softplus(beta=100, threshold=20) and its derivative (networks.py:85)
-__device__ __forceinline__ void softplus_fast(float z, float& y, float& d) {
+// Branch-free so that the 32 elements of a chunk pipeline through the MUFU unit (a per-element branch
+// serialises them: measured 5x slower, profiles/r1_tc_kernel.md).
+__device__ __forceinline__ float softplus_fast(float z) {
   float t = 100.f * z;
-  if (t > 20.f) {
-    y = z;
-    d = 1.f;
-  } else {
-    float u = __expf(t);
-    y = __logf(1.f + u) * 0.01f;
-    d = __fdividef(u, 1.f + u);
-  }
+  float u = __expf(fminf(t, 20.f));
+  float y = __logf(1.f + u) * 0.01f;
+  return t > 20.f ? z : y;
+}
+__device__ __forceinline__ void softplus_fast_grad(float z, float& y, float& d) {
+  float t = 100.f * z;
+  float u = __expf(fminf(t, 20.f));
+  float r = __fdividef(1.f, 1.f + u);
+  float ys = __logf(1.f + u) * 0.01f;
+  bool big = t > 20.f;
+  y = big ? z : ys;
+  d = big ? 1.f : u * r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,29 +382,50 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
         const int cbeg = half * 128, cend = cbeg + 128;
         for (int c = cbeg; c < cend; c += 32) {
           float v[32];
+          float4 s4[8];
+          const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
+          if (need_sig) {   // issue the sigma' loads before waiting on TMEM: they are the long-latency part
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
+          }
           tmem_ld32(t_row + (uint32_t)c, v);
           if (st.epi == EPI_SOFTPLUS) {
+            float4 b4[8];
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-              float4 b4 = __ldg((const float4*)(st.bias + c + 4 * g4));
-              float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-              float dd[4];
+            for (int g4 = 0; g4 < 8; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
+            if (st.flags & F_SAVE_SIG) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float z = fmaf(v[4 * g4 + j], isc, bb[j]);
-                softplus_fast(z, v[4 * g4 + j], dd[j]);
-              }
-              if (st.flags & F_SAVE_SIG)
+              for (int g4 = 0; g4 < 8; ++g4) {
+                float dd[4];
+                softplus_fast_grad(fmaf(v[4 * g4 + 0], isc, b4[g4].x), v[4 * g4 + 0], dd[0]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 1], isc, b4[g4].y), v[4 * g4 + 1], dd[1]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 2], isc, b4[g4].z), v[4 * g4 + 2], dd[2]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 3], isc, b4[g4].w), v[4 * g4 + 3], dd[3]);
                 sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+              }
+            } else {
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                v[4 * g4 + 0] = softplus_fast(fmaf(v[4 * g4 + 0], isc, b4[g4].x));
+                v[4 * g4 + 1] = softplus_fast(fmaf(v[4 * g4 + 1], isc, b4[g4].y));
+                v[4 * g4 + 2] = softplus_fast(fmaf(v[4 * g4 + 2], isc, b4[g4].z));
+                v[4 * g4 + 3] = softplus_fast(fmaf(v[4 * g4 + 3], isc, b4[g4].w));
+              }
             }
-            if (st.flags & F_INJECT_EMB) {
+            if ((st.flags & F_INJECT_EMB) && c + 32 > P.inj_col) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (c + j >= P.inj_col) v[j] = embed_elem(x, d, c + j - P.inj_col);
             }
             if (st.flags & F_SDF_DOT) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dot0 = fmaf(v[j], __ldg(P.w8row + c + j), dot0);
+              for (int g4 = 0; g4 < 8; ++g4) {
+                float4 w4 = __ldg((const float4*)(P.w8row + c + 4 * g4));
+                dot0 = fmaf(v[4 * g4 + 0], w4.x, dot0);
+                dot0 = fmaf(v[4 * g4 + 1], w4.y, dot0);
+                dot0 = fmaf(v[4 * g4 + 2], w4.z, dot0);
+                dot0 = fmaf(v[4 * g4 + 3], w4.w, dot0);
+              }
             }
           } else if (st.epi == EPI_FEAT) {
 #pragma unroll
@@ -409,41 +436,33 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
                 *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else if (st.epi == EPI_BWD) {
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-              int col = c + 4 * g4;
-              if ((st.flags & F_FINAL_GRAD)) {
-                // d / d embed of layer 0 : plain scaled accumulator (first E columns matter)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[4 * g4 + j] *= isc;
-              } else if ((st.flags & F_SKIP_GRAD) && col + 3 >= P.inj_col) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  int cc = col + j;
-                  float gval = v[4 * g4 + j] * isc;
-                  if (cc >= P.inj_col) {
-                    ge[(size_t)(cc - P.inj_col) * 128 + row] = gval;
-                    v[4 * g4 + j] = 0.f;
-                  } else {
-                    float4 s4 = sig[((size_t)st.sig * 64 + (col >> 2)) * 128 + row];
-                    float sg = j == 0 ? s4.x : (j == 1 ? s4.y : (j == 2 ? s4.z : s4.w));
-                    v[4 * g4 + j] = gval * sg;
-                  }
-                }
-              } else {
-                float4 s4 = sig[((size_t)st.sig * 64 + (col >> 2)) * 128 + row];
-                v[4 * g4 + 0] = v[4 * g4 + 0] * isc * s4.x;
-                v[4 * g4 + 1] = v[4 * g4 + 1] * isc * s4.y;
-                v[4 * g4 + 2] = v[4 * g4 + 2] * isc * s4.z;
-                v[4 * g4 + 3] = v[4 * g4 + 3] * isc * s4.w;
-              }
-            }
             if (st.flags & F_FINAL_GRAD) {
-              // park d/d embed (layer-0 part) next to the skip part: ge[E + k]... combined below
+              // d / d embed of layer 0 (first E columns matter): add to the parked skip gradient
               if (c < 128) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j];
+                  if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j] * isc;
+              }
+            } else if ((st.flags & F_SKIP_GRAD) && c + 32 > P.inj_col) {
+              // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
+              const float* s4f = reinterpret_cast<const float*>(s4);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float gval = v[j] * isc;
+                if (c + j >= P.inj_col) {
+                  ge[(size_t)(c + j - P.inj_col) * 128 + row] = gval;
+                  v[j] = 0.f;
+                } else {
+                  v[j] = gval * s4f[j];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                v[4 * g4 + 0] *= isc * s4[g4].x;
+                v[4 * g4 + 1] *= isc * s4[g4].y;
+                v[4 * g4 + 2] *= isc * s4[g4].z;
+                v[4 * g4 + 3] *= isc * s4[g4].w;
               }
             }
           } else {   // EPI_RELU

@@ -341,3 +341,43 @@ def make_hit_lists(scene, inputs, all_hit=False):
             c, h = person_box(person)
             out.append(ray_box_hits(cam, dirs, c, h))
     return out
+
+
+class SyntheticSMPLServer:
+    """Offline stand-in for lib/model/smpl.py:SMPLServer (needs the licence-gated SMPL pkl): same call
+    signature and output keys; the body is the capsule model above.  ``forward`` ignores betas (the
+    capsule body has no shape space) and applies scale / translation / pose exactly as smpl.py:50-95."""
+
+    def __init__(self, person_index=0, P=2):
+        self.p, self.P = person_index, P
+        verts_t, W = make_body(100 + person_index)
+        self._verts_t, self._W = verts_t, W
+        theta_c = np.zeros((24, 3))
+        theta_c[1, 2] = math.pi / 6
+        theta_c[2, 2] = -math.pi / 6
+        self._A_c = _rigid_transform(_rodrigues(theta_c), _J)
+        self._A_c_inv = np.linalg.inv(self._A_c)
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+        self.verts_c = f32(lbs_np(verts_t, W, self._A_c))[None]
+        self.weights = f32(W)[None]
+        self.scale = 1.0
+
+    def canonical_output(self):
+        return self(torch.ones(1), torch.zeros(1, 3), torch.zeros(1, 72), torch.zeros(1, 10))
+
+    def __call__(self, scale, transl, thetas, betas, absolute=False):
+        s = float(scale.reshape(-1)[0])
+        self.scale = s
+        t = transl.detach().cpu().double().numpy().reshape(3)
+        th = thetas.detach().cpu().double().numpy().reshape(24, 3)
+        A_p = _rigid_transform(_rodrigues(th), _J)
+        verts = s * lbs_np(self._verts_t, self._W, A_p) + t * s
+        tf = A_p.copy()
+        tf[:, :3, :] *= s
+        tf[:, :3, 3] += t * s
+        if not absolute:
+            tf = np.einsum("nij,njk->nik", tf, self._A_c_inv)
+        f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+        dev = thetas.device
+        return {"smpl_verts": f32(verts)[None].to(dev), "smpl_tfs": f32(tf)[None].to(dev),
+                "smpl_weights": self.weights.to(dev)}

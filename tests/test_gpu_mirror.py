@@ -1,0 +1,112 @@
+"""GPU: the host-side mirror of the reference operator surface (multiply_b200/model) — same class names,
+constructor options, state-dict keys and forward signatures as /root/reference/code/lib/model — checked
+against the CPU oracle and against the fused Renderer."""
+import math
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from multiply_b200 import scene as S
+
+OPT = dict(
+    with_bkgd=True, num_training_frames=75, dim_frame_encoding=32,
+    implicit_network=dict(feature_vector_size=256, d_in=3, d_out=1, dims=[256] * 8, init="geometry", bias=0.6,
+                          skip_in=[4], weight_norm=True, embedder_mode="fourier", multires=6, cond="smpl"),
+    rendering_network=dict(feature_vector_size=256, mode="pose_no_view", d_in=14, d_out=3, dims=[256] * 4,
+                           weight_norm=True, multires_view=-1),
+    bg_implicit_network=dict(feature_vector_size=256, d_in=4, d_out=1, dims=[256] * 8, init="none", bias=0.0,
+                             skip_in=[4], weight_norm=False, embedder_mode="fourier", multires=10, cond="frame"),
+    bg_rendering_network=dict(feature_vector_size=256, mode="nerf_frame_encoding", d_in=3, d_out=3, dims=[128],
+                              weight_norm=False, multires_view=4),
+    density=dict(params_init={"beta": 0.1}, beta_min=0.0001),
+    ray_sampler=dict(near=0.0, N_samples=16, N_samples_eval=32, N_samples_extra=8, eps=0.1, beta_iters=10,
+                     max_total_iters=5, N_samples_inverse_sphere=32, add_tiny=1.0e-6),
+)
+
+
+def _build(sc):
+    from multiply_b200.model.multiply import Multiply
+    P = len(sc["persons"])
+    servers = [S.SyntheticSMPLServer(p, P) for p in range(P)]
+    m = Multiply(OPT, smpl_server_list=servers)
+    sd = {}
+    for p, person in enumerate(sc["persons"]):
+        for k, v in person["implicit"].items():
+            sd[f"foreground_implicit_network_list.{p}.{k}"] = v
+        for k, v in person["render"].items():
+            sd[f"foreground_rendering_network_list.{p}.{k}"] = v
+    for k, v in sc["bg_implicit"].items():
+        sd["bg_implicit_network." + k] = v
+    for k, v in sc["bg_render"].items():
+        sd["bg_rendering_network." + k] = v
+    sd["density.beta"] = torch.tensor(sc["beta_param"])
+    fw = torch.zeros(75, 32)
+    fw[3] = sc["frame_code"][0]
+    sd["frame_latent_encoder.weight"] = fw
+    missing, unexpected = m.load_state_dict(sd, strict=True), None
+    return m.cuda().eval()
+
+
+def test_multiply_forward_drop_in():
+    """Multiply.forward(input) with the reference's input dict == oracle."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 96, seed=11, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    ref = port.multiply_forward(sc, inp, hits)
+    m = _build(sc)
+    P = 2
+    transl = torch.tensor([[0.8 * (p - (P - 1) / 2.0), 0.15, 0.3 * p] for p in range(P)])[None]
+    smpl_pose = torch.stack([sc["persons"][p]["smpl_pose"][0] for p in range(P)])[None]
+    smpl_params = torch.zeros(1, P, 86)
+    smpl_params[:, :, 0] = 0.5
+    inputs = dict(uv=inp["uv"].cuda(), pose=inp["pose"].cuda(), intrinsics=inp["intrinsics"].cuda(),
+                  smpl_params=smpl_params.cuda(), smpl_pose=smpl_pose.cuda(), smpl_shape=torch.zeros(1, P, 10).cuda(),
+                  smpl_trans=transl.cuda(), idx=torch.tensor([3]).cuda())
+    out = m(inputs)
+    torch.cuda.synchronize()
+    assert set(out) == {"acc_map", "acc_person_list", "rgb_values", "fg_rgb_values", "normal_values"}
+    for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4, k
+
+
+def test_operator_mirrors():
+    """ImplicitNet / RenderingNet / LaplaceDensity / SMPLDeformer / ErrorBoundSampler called the way the
+    reference calls them (networks.py:126, :263; density.py:11; deformer.py:19; ray_sampler.py:66)."""
+    from multiply_b200 import engine
+    from multiply_b200.model import networks, density, deformer
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    p0 = sc["persons"][0]
+    net = networks.ImplicitNet(OPT["implicit_network"])
+    net.load_state_dict(p0["implicit"], strict=True)
+    net = net.cuda().eval()
+    x = (torch.rand(300, 3, generator=torch.Generator().manual_seed(1)) - 0.5)
+    y = net(x.cuda(), {"smpl": p0["cond"].cuda()})
+    with torch.no_grad():
+        ref = port.implicit_forward(p0["implicit"], x, p0["cond"], 6)
+    assert y.shape == (1, 300, 257)
+    assert float((y[0].cpu() - ref).abs().max()) < 5e-5
+    rn = networks.RenderingNet(OPT["rendering_network"])
+    rn.load_state_dict(p0["render"], strict=True)
+    rn = rn.cuda().eval()
+    nrm = torch.nn.functional.normalize(torch.randn(300, 3, generator=torch.Generator().manual_seed(2)), dim=1)
+    rgb = rn(x.cuda(), nrm.cuda(), None, p0["cond"].cuda(), ref[:, 1:].cuda())
+    with torch.no_grad():
+        rref = port.rendering_forward(p0["render"], "pose_no_view", x, nrm, None, p0["cond"], ref[:, 1:])
+    assert float((rgb.cpu() - rref).abs().max()) < 1e-5
+    dens = density.LaplaceDensity(params_init={"beta": 0.1}, beta_min=1e-4).cuda()
+    s = torch.linspace(-0.5, 4.0, 100)
+    assert float((dens(s.cuda()).cpu() - port.laplace_density(s, port.get_beta(0.1))).abs().max()) < 1e-5
+    d = deformer.SMPLDeformer(smpl_verts=p0["verts_c"], smpl_weights=p0["weights"], scale=0.5)
+    pts = p0["verts_p"][:400] + 0.03
+    xc, outl = d.forward(pts.cuda(), p0["tfs"][None].cuda(), return_weights=False, inverse=True,
+                         smpl_verts=p0["verts_p"][None].cuda())
+    xr, orf = port.deform_inverse(pts, p0)
+    assert bool((outl.cpu() == orf).all()) and float((xc.cpu() - xr).abs().max()) < 1e-5
+    assert net(x[:0].cuda(), {"smpl": p0["cond"].cuda()}).shape[1] == 0      # zero-size early return
