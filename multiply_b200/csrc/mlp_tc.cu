@@ -18,6 +18,7 @@
 //     L8 features, the reverse sweep B7..B0 (d sdf / d x_c), normals, colour layers, RGB.
 #include "common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 namespace mp {
 
@@ -84,7 +85,7 @@ struct TcIO {
 constexpr size_t kSigBytes = (size_t)8 * 64 * 128 * 16;      // sigma' [8][64][128] float4
 constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo chunks
 constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
-constexpr size_t kMiscBytes = (size_t)128 * 16 * 4;          // partial sums / normals [128][16]
+constexpr size_t kMiscBytes = (size_t)128 * 32 * 4;          // partial sums / normals [128][32]
 constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes;
 
 // shared memory carve-up
@@ -203,7 +204,8 @@ __device__ __forceinline__ float embed_elem(const float* x, int d, int k) {
   return r < d ? sinf(t) : cosf(t);
 }
 
-__device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // softplus(beta=100, threshold=20) and its derivative (networks.py:85)
 // Branch-free so that the 32 elements of a chunk pipeline through the MUFU unit (a per-element branch
@@ -227,8 +229,31 @@ __device__ __forceinline__ void softplus_fast_grad(float z, float& y, float& d) 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
-                                                          const __grid_constant__ TcIO io) {
+template <int CW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// NW epilogue warps (8 or 16): warp w owns TMEM lane quadrant w % 4 (rows) and column part (w-2)/4.
+template <int NW>
+__global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
+                                                                   const __grid_constant__ TcIO io) {
+  constexpr int NPART = NW / 4;            // column parts
+  constexpr int PCOLS = 256 / NPART;       // columns per part
+  constexpr int CW = (NW == 16) ? 16 : 32; // columns per TMEM load (register budget)
+  constexpr int G4 = CW / 4;
+  constexpr int NEPI = 32 * NW;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
       mbar_init(&empty[i], 1);
     }
     mbar_init(d_full, 1);
-    mbar_init(a_ready, 256);
+    mbar_init(a_ready, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -325,16 +350,17 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;       // column half: 0 -> cols [0,128), 1 -> [128,256)
+    const int part = (warp - 2) >> 2;       // column part
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
     char* scr = io.scratch + (size_t)blockIdx.x * io.scratch_per_cta;
     float4* sig = (float4*)scr;                                  // [8][64][128]
     uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
     float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
-    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][16]
+    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
     uint32_t df_ph = 0;
     const int d = P.d_in, E = P.E;
+    const int cbeg = part * PCOLS, cend = cbeg + PCOLS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int pt = tile * 128 + row;
       const bool valid = pt < count;
@@ -344,9 +370,8 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
       const int slot = valid ? (io.slot ? io.slot[pt] : pt) : 0;
       // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
       {
-        const int nk0 = P.step[0].nk;
-        const int ncol = nk0 * 64;
-        const int c0 = half * (ncol / 2), c1 = c0 + ncol / 2;
+        const int ncol = P.step[0].nk * 64;
+        const int c0 = part * (ncol / NPART), c1 = c0 + ncol / NPART;
         for (int c = c0; c < c1; c += 8) {
           float v[8];
 #pragma unroll
@@ -364,7 +389,6 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
         float dv[3] = {0.f, 0.f, 0.f};
         if (valid)
           for (int a = 0; a < 3; ++a) dv[a] = io.extra[(size_t)pt * 3 + a];
-#pragma unroll
         for (int e = 0; e < 27; ++e) xin[e] = embed_elem(dv, 3, e);
       } else {
         xin[0] = x[0];
@@ -377,25 +401,24 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
         mbar_wait(d_full, df_ph);
         df_ph ^= 1;
         tc_fence_after();
-        if (st.flags & F_FINAL_GRAD) ep_bar();           // skip-gradient parked by the other column half
+        if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
-        const int cbeg = half * 128, cend = cbeg + 128;
-        for (int c = cbeg; c < cend; c += 32) {
-          float v[32];
-          float4 s4[8];
+        for (int c = cbeg; c < cend; c += CW) {
+          float v[CW];
+          float4 s4[G4];
           const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
           if (need_sig) {   // issue the sigma' loads before waiting on TMEM: they are the long-latency part
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
+            for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
           }
-          tmem_ld32(t_row + (uint32_t)c, v);
+          tmem_ld<CW>(t_row + (uint32_t)c, v);
           if (st.epi == EPI_SOFTPLUS) {
-            float4 b4[8];
+            float4 b4[G4];
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
+            for (int g4 = 0; g4 < G4; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
             if (st.flags & F_SAVE_SIG) {
 #pragma unroll
-              for (int g4 = 0; g4 < 8; ++g4) {
+              for (int g4 = 0; g4 < G4; ++g4) {
                 float dd[4];
                 softplus_fast_grad(fmaf(v[4 * g4 + 0], isc, b4[g4].x), v[4 * g4 + 0], dd[0]);
                 softplus_fast_grad(fmaf(v[4 * g4 + 1], isc, b4[g4].y), v[4 * g4 + 1], dd[1]);
@@ -405,21 +428,21 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
               }
             } else {
 #pragma unroll
-              for (int g4 = 0; g4 < 8; ++g4) {
+              for (int g4 = 0; g4 < G4; ++g4) {
                 v[4 * g4 + 0] = softplus_fast(fmaf(v[4 * g4 + 0], isc, b4[g4].x));
                 v[4 * g4 + 1] = softplus_fast(fmaf(v[4 * g4 + 1], isc, b4[g4].y));
                 v[4 * g4 + 2] = softplus_fast(fmaf(v[4 * g4 + 2], isc, b4[g4].z));
                 v[4 * g4 + 3] = softplus_fast(fmaf(v[4 * g4 + 3], isc, b4[g4].w));
               }
             }
-            if ((st.flags & F_INJECT_EMB) && c + 32 > P.inj_col) {
+            if ((st.flags & F_INJECT_EMB) && c + CW > P.inj_col) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
+              for (int j = 0; j < CW; ++j)
                 if (c + j >= P.inj_col) v[j] = embed_elem(x, d, c + j - P.inj_col);
             }
             if (st.flags & F_SDF_DOT) {
 #pragma unroll
-              for (int g4 = 0; g4 < 8; ++g4) {
+              for (int g4 = 0; g4 < G4; ++g4) {
                 float4 w4 = __ldg((const float4*)(P.w8row + c + 4 * g4));
                 dot0 = fmaf(v[4 * g4 + 0], w4.x, dot0);
                 dot0 = fmaf(v[4 * g4 + 1], w4.y, dot0);
@@ -429,10 +452,16 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
             }
           } else if (st.epi == EPI_FEAT) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], isc, __ldg(st.bias + c + j));
+            for (int g4 = 0; g4 < G4; ++g4) {
+              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
+              v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
+              v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
+              v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
+              v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
+            }
             if ((st.flags & F_FEAT_OUT) && io.feat_out && valid) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
+              for (int j = 0; j < CW; j += 4)
                 *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else if (st.epi == EPI_BWD) {
@@ -440,14 +469,14 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
               // d / d embed of layer 0 (first E columns matter): add to the parked skip gradient
               if (c < 128) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < CW; ++j)
                   if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j] * isc;
               }
-            } else if ((st.flags & F_SKIP_GRAD) && c + 32 > P.inj_col) {
+            } else if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
               // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
               const float* s4f = reinterpret_cast<const float*>(s4);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
+              for (int j = 0; j < CW; ++j) {
                 float gval = v[j] * isc;
                 if (c + j >= P.inj_col) {
                   ge[(size_t)(c + j - P.inj_col) * 128 + row] = gval;
@@ -458,7 +487,7 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
               }
             } else {
 #pragma unroll
-              for (int g4 = 0; g4 < 8; ++g4) {
+              for (int g4 = 0; g4 < G4; ++g4) {
                 v[4 * g4 + 0] *= isc * s4[g4].x;
                 v[4 * g4 + 1] *= isc * s4[g4].y;
                 v[4 * g4 + 2] *= isc * s4[g4].z;
@@ -467,43 +496,49 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
             }
           } else {   // EPI_RELU
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], isc, __ldg(st.bias + c + j));
+            for (int g4 = 0; g4 < G4; ++g4) {
+              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
+              v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
+              v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
+              v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
+              v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
+            }
             if (st.flags & F_EXTRA_IN) {
+              for (int e = 0; e < P.n_extra; ++e) {
+                const float xe = xin[e];
+                const float4* w4 = (const float4*)(P.W0x + e * 256 + c);
 #pragma unroll
-              for (int e = 0; e < 27; ++e) {
-                if (e < P.n_extra) {
-                  const float xe = xin[e];
-                  const float4* w4 = (const float4*)(P.W0x + e * 256 + c);
-#pragma unroll
-                  for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 ww = __ldg(w4 + j4);
-                    v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
-                    v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
-                    v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
-                    v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
-                  }
+                for (int j4 = 0; j4 < G4; ++j4) {
+                  float4 ww = __ldg(w4 + j4);
+                  v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
+                  v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
+                  v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
+                  v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
                 }
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
             if (st.flags & F_RGB_OUT) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                dot0 = fmaf(v[j], __ldg(P.Wrgb + c + j), dot0);
-                dot1 = fmaf(v[j], __ldg(P.Wrgb + 256 + c + j), dot1);
-                dot2 = fmaf(v[j], __ldg(P.Wrgb + 512 + c + j), dot2);
+              for (int g4 = 0; g4 < G4; ++g4) {
+                float4 w0 = __ldg((const float4*)(P.Wrgb + c + 4 * g4));
+                float4 w1 = __ldg((const float4*)(P.Wrgb + 256 + c + 4 * g4));
+                float4 w2 = __ldg((const float4*)(P.Wrgb + 512 + c + 4 * g4));
+                dot0 = fmaf(v[4 * g4 + 0], w0.x, fmaf(v[4 * g4 + 1], w0.y, fmaf(v[4 * g4 + 2], w0.z, fmaf(v[4 * g4 + 3], w0.w, dot0))));
+                dot1 = fmaf(v[4 * g4 + 0], w1.x, fmaf(v[4 * g4 + 1], w1.y, fmaf(v[4 * g4 + 2], w1.z, fmaf(v[4 * g4 + 3], w1.w, dot1))));
+                dot2 = fmaf(v[4 * g4 + 0], w2.x, fmaf(v[4 * g4 + 1], w2.y, fmaf(v[4 * g4 + 2], w2.z, fmaf(v[4 * g4 + 3], w2.w, dot2))));
               }
             }
           }
           // activations of this chunk -> A (fp16 hi/lo, swizzled) unless this is the last layer
           if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) store_a8(A, row, c + j, v + j);
+            for (int j = 0; j < CW; j += 8) store_a8(A, row, c + j, v + j);
             if (st.epi == EPI_FEAT && (s + 1 < P.nsteps)) {
               // stash the feature chunks (they come back as the colour net's input)
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
+              for (int j = 0; j < CW; j += 8) {
                 uint4 hi, lo;
                 split8(v + j, hi, lo);
                 int chunk = (c + j) >> 3;
@@ -516,30 +551,34 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
         tc_fence_before();
         // ---- step-specific tails ----
         if (st.flags & F_SDF_DOT) {
-          misc[row * 16 + half] = dot0;
+          misc[row * 32 + part] = dot0;
           __threadfence_block();
-          ep_bar();
-          if (half == 0 && valid && io.sdf_out) io.sdf_out[slot] = misc[row * 16] + misc[row * 16 + 1] + __ldg(P.b8);
-          ep_bar();
+          ep_bar<NEPI>();
+          if (part == 0 && valid && io.sdf_out) {
+            float sacc = __ldg(P.b8);
+#pragma unroll
+            for (int pp = 0; pp < NPART; ++pp) sacc += misc[row * 32 + pp];
+            io.sdf_out[slot] = sacc;
+          }
+          ep_bar<NEPI>();
         }
         if (st.flags & F_SEED_BWD) {
           // A = W8[0,:] * sigma'_7    (d sdf / d z7)
           for (int c = cbeg; c < cend; c += 8) {
             float4 s0 = sig[((size_t)7 * 64 + (c >> 2)) * 128 + row];
             float4 s1 = sig[((size_t)7 * 64 + (c >> 2) + 1) * 128 + row];
-            float v[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= __ldg(P.w8row + c + j);
+            float4 wa = __ldg((const float4*)(P.w8row + c));
+            float4 wb = __ldg((const float4*)(P.w8row + c + 4));
+            float v[8] = {s0.x * wa.x, s0.y * wa.y, s0.z * wa.z, s0.w * wa.w,
+                          s1.x * wb.x, s1.y * wb.y, s1.z * wb.z, s1.w * wb.w};
             store_a8(A, row, c, v);
           }
         }
-        if (st.flags & F_SKIP_GRAD) {
-          __threadfence_block();
-        }
+        if (st.flags & F_SKIP_GRAD) __threadfence_block();
         if (st.flags & F_FINAL_GRAD) {
           __threadfence_block();
-          ep_bar();
-          if (half == 0) {
+          ep_bar<NEPI>();
+          if (part == 0) {
             // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos)
             float g[3] = {0.f, 0.f, 0.f};
             for (int a = 0; a < d && a < 3; ++a) {
@@ -576,15 +615,15 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
                 io.nrm_out[3 * (size_t)slot + 2] = n2;
               }
             }
-            misc[row * 16 + 4] = n0;
-            misc[row * 16 + 5] = n1;
-            misc[row * 16 + 6] = n2;
+            misc[row * 32 + 4] = n0;
+            misc[row * 32 + 5] = n1;
+            misc[row * 32 + 6] = n2;
           }
           __threadfence_block();
-          ep_bar();
-          xin[3] = misc[row * 16 + 4];
-          xin[4] = misc[row * 16 + 5];
-          xin[5] = misc[row * 16 + 6];
+          ep_bar<NEPI>();
+          xin[3] = misc[row * 32 + 4];
+          xin[4] = misc[row * 32 + 5];
+          xin[5] = misc[row * 32 + 6];
           // features back into A for the colour net
           if (s + 1 < P.nsteps) {
             for (int c = cbeg; c < cend; c += 8) {
@@ -596,19 +635,21 @@ __global__ void __launch_bounds__(320, 1) tc_chain_kernel(const __grid_constant_
           }
         }
         if (st.flags & F_RGB_OUT) {
-          misc[row * 16 + 8 + half * 4 + 0] = dot0;
-          misc[row * 16 + 8 + half * 4 + 1] = dot1;
-          misc[row * 16 + 8 + half * 4 + 2] = dot2;
+          misc[row * 32 + 8 + part * 3 + 0] = dot0;
+          misc[row * 32 + 8 + part * 3 + 1] = dot1;
+          misc[row * 32 + 8 + part * 3 + 2] = dot2;
           __threadfence_block();
-          ep_bar();
-          if (half == 0 && valid && io.rgb_out) {
+          ep_bar<NEPI>();
+          if (part == 0 && valid && io.rgb_out) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              float z = misc[row * 16 + 8 + k] + misc[row * 16 + 12 + k] + __ldg(P.brgb + k);
+              float z = __ldg(P.brgb + k);
+#pragma unroll
+              for (int pp = 0; pp < NPART; ++pp) z += misc[row * 32 + 8 + pp * 3 + k];
               io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
             }
           }
-          ep_bar();
+          ep_bar<NEPI>();
         }
         // hand A (and the drained accumulator) to the MMA warp for the next step of this tile;
         // the last step's hand-over is the next tile's prologue arrival
@@ -739,6 +780,7 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   float* w8row = a.take<float>(256);
   float* W0x = a.take<float>(32 * 256);
   float* Wrgb = a.take<float>(3 * 256);
+  float* b8feat = a.take<float>(256);      // b8[1:], 16-byte aligned copy (the epilogue loads float4)
   MP_REQUIRE(a.ok, "tc_pack: storage too small");
   MP_CHECK_CUDA(cudaMemsetAsync(c.blob, 0, (size_t)170 * kSlotBytes, st));
   TcProgram P;
@@ -755,6 +797,8 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   P.Wrgb = Wrgb;
   P.n_extra = f.ren_extra;
   copy_strided_kernel<<<1, 256, 0, st>>>(f.imp_W[8], 1, 256, w8row);     // W8[0,:]
+  g_launches++;
+  copy_strided_kernel<<<1, 256, 0, st>>>(f.imp_b[8] + 1, 1, 256, b8feat);
   g_launches++;
   int s = 0;
   const int nk0 = (E + 63) / 64;
@@ -782,7 +826,7 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   P.step[s].epi = EPI_FEAT;
   P.step[s].flags = F_FEAT_OUT;
   P.step[s].sig = -1;
-  P.step[s].bias = f.imp_b[8] + 1;
+  P.step[s].bias = b8feat;
   P.step[s].ncols = 256;
   ++s;
   tb->fwd_prog = P;
@@ -924,8 +968,12 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
   io.scratch = (char*)ws;
   io.scratch_per_cta = kScratchPerCta;
   static bool attr_set = false;
+  static int nw = 16;
   if (!attr_set) {
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const char* e = getenv("MP_TC_EPI_WARPS");
+    if (e && atoi(e) == 8) nw = 8;
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   ProfEntry pe;
@@ -942,7 +990,10 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
     }
     MP_CHECK_CUDA(cudaEventRecord(pe.e0, st));
   }
-  tc_chain_kernel<<<grid, 320, kSmemBytes, st>>>(P, io);
+  if (nw == 16)
+    tc_chain_kernel<16><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
+  else
+    tc_chain_kernel<8><<<grid, 64 + 32 * 8, kSmemBytes, st>>>(P, io);
   MP_LAUNCH_CHECK();
   if (prof) {
     MP_CHECK_CUDA(cudaEventRecord(pe.e1, st));

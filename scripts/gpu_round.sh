@@ -4,4 +4,5 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
 timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_tc.json
+MP_TC_EPI_WARPS=8 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_tc_w8.json
 MP_ENGINE=simt timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_simt.json
