@@ -156,7 +156,7 @@ int launch_deform_rays(const Body& b, const float* dirs, const float* cam, const
                        int sdf_stride, float* xc_list, int* slot_list, int* count, uint8_t* outlier_out,
                        const int* active, cudaStream_t st);
 int launch_forward_jac(const Body& b, const float* x_c, int N, const int* n_dev, float* x_d, float* Jinv,
-                       cudaStream_t st);
+                       int jstride, cudaStream_t st);
 
 }  // namespace mp
 

@@ -57,11 +57,13 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restric
       ext = fmaxf(ext, h - l);
     }
     float h = cell;
-    // keep the grid within kMaxCells
+    // Two empty border cells on every side: a query within 2h of the vertex bounding box still has its own
+    // cell inside the grid, which is what the optimality proof of nearest_vertex() needs.  Keep the grid
+    // within kMaxCells.
     for (;;) {
       long long n = 1;
       for (int a = 0; a < 3; ++a) {
-        g.dim[a] = (int)floorf((s_hi[a][0] - g.lo[a]) / h) + 1;
+        g.dim[a] = (int)floorf((s_hi[a][0] - g.lo[a]) / h) + 1 + 4;
         n *= g.dim[a];
       }
       if (n <= kMaxCells) {
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restric
       }
       h *= 1.25f;
     }
+    for (int a = 0; a < 3; ++a) g.lo[a] -= 2.f * h;
     g.h = h;
     g.inv_h = 1.0f / h;
     *hdr = g;
@@ -136,17 +139,39 @@ __device__ __forceinline__ void nn_consider(const float4 v, float px, float py, 
 // Returns the nearest vertex index and squared distance.  `found_exact` is true when the grid
 // neighbourhood proves the result is the global arg-min (best distance <= h); otherwise the
 // caller may request a full scan.
+// Scan the (2R+1)^3 block of cells around (cx,cy,cz), nearest cells first in z/y, skipping every cell whose
+// box is provably farther than the best distance found so far (the box distance carries a safety margin so a
+// cell holding an equally distant vertex is never skipped: ties must still resolve to the lowest index).
 __device__ __forceinline__ void scan_block(const GridHeader& g, const int* __restrict__ cell_start,
                                            const float4* __restrict__ sorted, int cx, int cy, int cz, int R, float px,
                                            float py, float pz, float& best, int& bi) {
-  int x0 = max(cx - R, 0), x1 = min(cx + R, g.dim[0] - 1);
-  if (x0 > x1) return;
-  for (int z = max(cz - R, 0); z <= min(cz + R, g.dim[2] - 1); ++z)
-    for (int y = max(cy - R, 0); y <= min(cy + R, g.dim[1] - 1); ++y) {
+  const float qx = px - g.lo[0], qy = py - g.lo[1], qz = pz - g.lo[2];
+  for (int dz = 0; dz <= 2 * R; ++dz) {
+    // visiting order 0, -1, +1, -2, +2 ...
+    int oz = (dz + 1) >> 1;
+    int z = cz + ((dz & 1) ? -oz : oz);
+    if (z < 0 || z >= g.dim[2]) continue;
+    float ez = fmaxf(fmaxf(z * g.h - qz, qz - (z + 1) * g.h), 0.f);
+    for (int dy = 0; dy <= 2 * R; ++dy) {
+      int oy = (dy + 1) >> 1;
+      int y = cy + ((dy & 1) ? -oy : oy);
+      if (y < 0 || y >= g.dim[1]) continue;
+      float ey = fmaxf(fmaxf(y * g.h - qy, qy - (y + 1) * g.h), 0.f);
+      float dzy = ez * ez + ey * ey;
+      if (dzy * 0.9999f - 1e-9f > best) continue;
       int base = (z * g.dim[1] + y) * g.dim[0];
-      int b = cell_start[base + x0], e = cell_start[base + x1 + 1];
-      for (int j = b; j < e; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
+      for (int dx = 0; dx <= 2 * R; ++dx) {
+        int ox = (dx + 1) >> 1;
+        int x = cx + ((dx & 1) ? -ox : ox);
+        if (x < 0 || x >= g.dim[0]) continue;
+        float ex = fmaxf(fmaxf(x * g.h - qx, qx - (x + 1) * g.h), 0.f);
+        float dc = dzy + ex * ex;
+        if (dc * 0.9999f - 1e-9f > best) continue;
+        int b = cell_start[base + x], e = cell_start[base + x + 1];
+        for (int j = b; j < e; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
+      }
     }
+  }
 }
 
 __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* __restrict__ cell_start,
@@ -160,24 +185,26 @@ __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* _
   fy = fminf(fmaxf(fy, -4.f), (float)g.dim[1] + 4.f);
   fz = fminf(fmaxf(fz, -4.f), (float)g.dim[2] + 4.f);
   int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
-  scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
   // Everything outside the (2R+1)^3 block is farther than R*h from the query (when the query's own
   // cell lies inside the grid), so best <= (R*h)^2 proves global optimality.
   bool inside = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.dim[0] && cy < g.dim[1] && cz < g.dim[2];
   float hh = g.h * 0.999f;
+  if (!full_scan_if_unsure) {
+    // outlier classification only: any vertex within the 0.1 radius lies in the 3x3x3 block (cell >= 0.1001)
+    scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
+    return;
+  }
+  scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
   bool proven = inside && best <= hh * hh;
-  if (!proven && full_scan_if_unsure) {
-    if (inside) {
-      best = INFINITY;
-      bi = 0x7fffffff;
-      scan_block(g, cell_start, sorted, cx, cy, cz, 2, px, py, pz, best, bi);
-      proven = best <= 4.f * hh * hh;
-    }
-    if (!proven) {
-      best = INFINITY;
-      bi = 0x7fffffff;
-      for (int j = 0; j < V; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
-    }
+  if (!proven && inside) {
+    // the 3x3x3 block proved nothing: widen to 5x5x5 (the scan keeps `best`, so already-pruned cells stay pruned)
+    scan_block(g, cell_start, sorted, cx, cy, cz, 2, px, py, pz, best, bi);
+    proven = best <= 4.f * hh * hh;
+  }
+  if (!proven) {
+    best = INFINITY;
+    bi = 0x7fffffff;
+    for (int j = 0; j < V; ++j) nn_consider(__ldg(&sorted[j]), px, py, pz, best, bi);
   }
 }
 
@@ -187,13 +214,20 @@ __device__ __forceinline__ void blend_tf(const float* __restrict__ w, const floa
 #pragma unroll
   for (int k = 0; k < 12; ++k) T[k] = 0.f;
   s = 0.f;
-  for (int j = 0; j < MP_NUM_JOINTS; ++j) {
-    float wj = __ldg(&w[j]);
-    if (wj == 0.f) continue;   // adding 0*finite leaves the fp32 sum unchanged
-    const float* t = tfs + 16 * j;
+  const float4* w4 = reinterpret_cast<const float4*>(w);     // rows of 24 floats are 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = fmaf(wj, __ldg(&t[k]), T[k]);
-    s = fmaf(wj, __ldg(&t[15]), s);
+  for (int j4 = 0; j4 < MP_NUM_JOINTS / 4; ++j4) {
+    float4 ww = __ldg(w4 + j4);
+    float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float wj = wv[u];
+      if (wj == 0.f) continue;   // adding 0*finite leaves the fp32 sum unchanged
+      const float* t = tfs + 16 * (4 * j4 + u);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) T[k] = fmaf(wj, __ldg(&t[k]), T[k]);
+      s = fmaf(wj, __ldg(&t[15]), s);
+    }
   }
 }
 
@@ -310,7 +344,7 @@ __global__ void deform_rays_kernel(Body b, const float* __restrict__ dirs, const
 // forward skinning Jacobian: weights from the nearest CANONICAL vertex (deformer.py:31-35);
 // J = (sum_j w_j tfs_j)[:3,:3] because the weights are detached (deformer.py:47).
 __global__ void deform_forward_jac_kernel(Body b, const float* __restrict__ x_c, int N, const int* __restrict__ n_dev,
-                                          float* __restrict__ x_d, float* __restrict__ Jinv) {
+                                          float* __restrict__ x_d, float* __restrict__ Jinv, int jstride) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int n = n_dev ? *n_dev : N;
   if (i >= n) return;
@@ -329,8 +363,15 @@ __global__ void deform_forward_jac_kernel(Body b, const float* __restrict__ x_c,
   if (Jinv) {
     float I[9];
     inv3(T, 4, I);
+    if (jstride == 12) {   // padded rows: three 128-bit stores
+      float4* o = reinterpret_cast<float4*>(Jinv + 12 * (size_t)i);
+      o[0] = make_float4(I[0], I[1], I[2], I[3]);
+      o[1] = make_float4(I[4], I[5], I[6], I[7]);
+      o[2] = make_float4(I[8], 0.f, 0.f, 0.f);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Jinv[9 * (size_t)i + k] = I[k];
+      for (int k = 0; k < 9; ++k) Jinv[9 * (size_t)i + k] = I[k];
+    }
   }
 }
 
@@ -355,9 +396,9 @@ int launch_deform_rays(const Body& b, const float* dirs, const float* cam, const
 }
 
 int launch_forward_jac(const Body& b, const float* x_c, int N, const int* n_dev, float* x_d, float* Jinv,
-                       cudaStream_t st) {
+                       int jstride, cudaStream_t st) {
   if (N <= 0) return 0;
-  deform_forward_jac_kernel<<<div_up(N, 128), 128, 0, st>>>(b, x_c, N, n_dev, x_d, Jinv);
+  deform_forward_jac_kernel<<<div_up(N, 128), 128, 0, st>>>(b, x_c, N, n_dev, x_d, Jinv, jstride);
   MP_LAUNCH_CHECK();
   return 0;
 }
@@ -436,6 +477,6 @@ int mp_deform_inverse(mp_body_t* h, const float* x, int N, float* x_c, uint8_t* 
 
 int mp_deform_forward_jac(mp_body_t* h, const float* x_c, int N, float* x_d, float* Jinv, void* stream) {
   MP_REQUIRE(h && h->b.tfs, "mp_deform_forward_jac: body has no pose (call mp_body_set_pose)");
-  return mp::launch_forward_jac(h->b, x_c, N, nullptr, x_d, Jinv, (cudaStream_t)stream);
+  return mp::launch_forward_jac(h->b, x_c, N, nullptr, x_d, Jinv, 9, (cudaStream_t)stream);
 }
 }

@@ -190,7 +190,7 @@ __global__ void normal_colour_input_kernel(const float* __restrict__ xc, const f
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int n = n_dev ? min(N, *n_dev) : N;
   if (i >= n) return;
-  const float* J = Jinv + 9 * (size_t)i;
+  const float* J = Jinv + 12 * (size_t)i;
   float g0 = grad[3 * i], g1 = grad[3 * i + 1], g2 = grad[3 * i + 2];
   // einsum('bi,bij->bj', gradients, grads_inv)
   float v0 = g0 * J[0] + g1 * J[3] + g2 * J[6];
@@ -368,7 +368,7 @@ int simt_shade_list(const Field& f, const float* xc_list, const int* slot_list, 
     if (!Jinv_list) continue;
     // ---- normals + colour ----------------------------------------------------------------
     const int ldc = 6 + 256;
-    normal_colour_input_kernel<<<div_up(n, 128), 128, 0, st>>>(x, gradp, Jinv_list + 9 * (size_t)s, featp, n, nrem,
+    normal_colour_input_kernel<<<div_up(n, 128), 128, 0, st>>>(x, gradp, Jinv_list + 12 * (size_t)s, featp, n, nrem,
                                                                b.cin, ldc, b.ntmp);
     MP_LAUNCH_CHECK();
     copy_cols_kernel<<<div_up(n * 256, 256), 256, 0, st>>>(featp, 256, 0, 256, n, nrem, b.cin, ldc, 6);

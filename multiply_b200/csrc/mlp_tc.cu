@@ -70,7 +70,7 @@ struct TcIO {
   const int* slot;       // [cap] output slot of each point or nullptr (identity)
   const int* count;      // device count or nullptr (= cap)
   int cap;
-  const float* jinv;     // [cap, 9] or nullptr
+  const float* jinv;     // [cap, 12] (3x3 row-major, padded to three float4) or nullptr
   const float* extra;    // [cap, n_extra] extra colour inputs (background view embedding) or nullptr
   float* sdf_out;        // scattered by slot
   float* rgb_out;        // [slots,3]
@@ -229,12 +229,26 @@ __device__ __forceinline__ void softplus_fast_grad(float z, float& y, float& d) 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// tcgen05.ld is asynchronous: `tmem_issue` starts the load of CW columns of this thread's row, `tmem_wait`
+// (tcgen05.wait::ld) makes the registers valid.  The wait lists the destination registers as in/out
+// operands so the compiler cannot touch them between the two.
 template <int CW>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+__device__ __forceinline__ void tmem_issue(uint32_t taddr, float* v);
 template <>
-__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_issue<32>(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 template <>
-__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_issue<16>(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -242,7 +256,29 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int CW>
+__device__ __forceinline__ void tmem_wait(float* v);
+template <>
+__device__ __forceinline__ void tmem_wait<16>(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_wait<32>(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // NW epilogue warps (8 or 16): warp w owns TMEM lane quadrant w % 4 (rows) and column part (w-2)/4.
@@ -403,15 +439,15 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         tc_fence_after();
         if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
-        for (int c = cbeg; c < cend; c += CW) {
-          float v[CW];
+        float va[CW];
+        auto process_chunk = [&](float* v, float* vnext, const int c) {
           float4 s4[G4];
           const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
           if (need_sig) {   // issue the sigma' loads before waiting on TMEM: they are the long-latency part
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
           }
-          tmem_ld<CW>(t_row + (uint32_t)c, v);
+          tmem_wait<CW>(v);
           if (st.epi == EPI_SOFTPLUS) {
             float4 b4[G4];
 #pragma unroll
@@ -547,6 +583,11 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               }
             }
           }
+        };
+        // (double-buffering the TMEM reads was measured slower: +20 % kernel time from spills / code size)
+        for (int c = cbeg; c < cend; c += CW) {
+          tmem_issue<CW>(t_row + (uint32_t)c, va);
+          process_chunk(va, va, c);
         }
         tc_fence_before();
         // ---- step-specific tails ----
@@ -601,7 +642,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             }
             float n0 = 0.f, n1 = 0.f, n2 = 0.f;
             if (io.jinv && valid) {
-              const float* J = io.jinv + 9 * (size_t)pt;
+              const float* J = io.jinv + 12 * (size_t)pt;
               float v0 = g[0] * J[0] + g[1] * J[3] + g[2] * J[6];
               float v1 = g[0] * J[1] + g[1] * J[4] + g[2] * J[7];
               float v2 = g[0] * J[2] + g[1] * J[5] + g[2] * J[8];

@@ -133,7 +133,7 @@ static bool render_carve(Arena& a, const mp_scene_t& sc, int R, RenderWs& w) {
     b.rgb = a.take<float>((size_t)Rp * n * 3);
     b.nrm = a.take<float>((size_t)Rp * n * 3);
     b.xc_list = a.take<float>((size_t)Rp * n * 3);
-    b.jinv = a.take<float>((size_t)Rp * n * 9);
+    b.jinv = a.take<float>((size_t)Rp * n * 12);
     b.slot_list = a.take<int>((size_t)Rp * n);
     b.count = a.take<int>(1);
     b.row_of_ray = a.take<int>(R);
@@ -258,7 +258,7 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
     MP_CHECK_CUDA(cudaMemsetAsync(b.nrm, 0, (size_t)Rp * n * 3 * sizeof(float), st));
     MP_TRY(launch_deform_rays(body, b.dirs, b.cam, b.z, n + 1, nullptr, 0, n, Rp, prune, b.sdf, n, b.xc_list,
                               b.slot_list, b.count, b.outl, nullptr, st));
-    MP_TRY(launch_forward_jac(body, b.xc_list, Rp * n, b.count, nullptr, b.jinv, st));
+    MP_TRY(launch_forward_jac(body, b.xc_list, Rp * n, b.count, nullptr, b.jinv, 12, st));
     MP_TRY(field_shade_list(field, b.xc_list, b.slot_list, b.count, Rp * n, b.jinv, b.sdf, b.rgb, b.nrm, nullptr,
                             nullptr, w.sub, w.sub_bytes, st));
     if (!prune) {
