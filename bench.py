@@ -97,6 +97,22 @@ def config_dict(world):
             "parallelism": "ray blocks sharded over %d GPU(s), one NCCL all_gather of pixels" % world}
 
 
+def best_cpu_threads(fn):
+    """The oracle is many small torch ops: using every host thread is often slower than a moderate count.
+    Time one call at a few settings and keep the fastest ("all the host threads it can use")."""
+    cores = os.cpu_count() or 1
+    best = None
+    for t in sorted({min(cores, 8), min(cores, 32), cores}):
+        torch.set_num_threads(t)
+        t0 = time.time()
+        fn()
+        dt = time.time() - t0
+        if best is None or dt < best[1]:
+            best = (t, dt)
+    torch.set_num_threads(best[0])
+    return best[0]
+
+
 def run_reference(args, rank, world):
     """The reference algorithm on the host CPU (oracle/port.py — pinned against the unmodified reference
     modules by tests/golden; the reference itself needs the absent SMPL pkl / trimesh / nerfacc / pytorch3d)."""
@@ -104,13 +120,14 @@ def run_reference(args, rank, world):
         return
     from oracle import port
     from multiply_b200 import scene as S
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sc = S.make_scene(P=PERSONS, S=S_SAMPLES, seed=42)
     n_sample = 48
     inp = S.make_rays(sc, RAYS_PER_GPU, seed=1234, region="boxes")
     sub = dict(uv=inp["uv"][:, :n_sample].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
     hits = S.make_hit_lists(sc, sub)
+    tiny = dict(uv=inp["uv"][:, :8].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
+    thits = S.make_hit_lists(sc, tiny)
+    cores = best_cpu_threads(lambda: port.multiply_forward(sc, tiny, thits))
     times = []
     for i in range(args.warmup + args.steps):
         t = time.time()
@@ -123,7 +140,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(world),
+            "config": dict(config_dict(world), precision="fp32 (torch CPU)", parallelism="host CPU, %d torch threads" % cores),
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
                              "sample": "%d of the %d rays of the same batch per step (full per-ray work: "
                                        "2 persons, S/E/X=128/256/64, background)" % (n_sample, RAYS_PER_GPU)},
@@ -153,7 +170,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from multiply_b200 import engine, _lib as L
+    from multiply_b200 import engine, parallel, _lib as L
     lib = L.lib()
     engine.set_engine(args.engine)
     sc, inp, hits = build_workload(rank, world)
@@ -165,15 +182,13 @@ def main():
     h_inp = {k: v.pin_memory() for k, v in inp.items()}
     h_hits = [h.pin_memory() for h in hits]
     h_out = torch.empty(R, 3).pin_memory()
-    gathered = torch.empty(world * R, 10, device=dev) if world > 1 else None
+    gathered = torch.empty(world * R, 10 + PERSONS, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step_resident():
         o = r.render(d_inp, d_hits)
         if world > 1:
-            px = torch.cat([o["rgb_values"], o["normal_values"], o["acc_map"][:, None],
-                            o["acc_person_list"], o["fg_rgb_values"][:, :1]], 1).contiguous()
-            dist.all_gather_into_tensor(gathered, px)
+            dist.all_gather_into_tensor(gathered, parallel.pack_pixels(o))
         return o
 
     def step_e2e():
@@ -181,9 +196,7 @@ def main():
         dh = [h.to(dev, non_blocking=True) for h in h_hits]
         o = r.render(di, dh)
         if world > 1:
-            px = torch.cat([o["rgb_values"], o["normal_values"], o["acc_map"][:, None],
-                            o["acc_person_list"], o["fg_rgb_values"][:, :1]], 1).contiguous()
-            dist.all_gather_into_tensor(gathered, px)
+            dist.all_gather_into_tensor(gathered, parallel.pack_pixels(o))
         h_out.copy_(o["rgb_values"], non_blocking=True)
         return o
 
@@ -283,11 +296,12 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import port
             from multiply_b200 import scene as S
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
             n_sample = 48
             sub = dict(uv=inp["uv"][:, :n_sample].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
             shits = S.make_hit_lists(sc, sub)
+            tiny = dict(uv=inp["uv"][:, :8].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
+            thits = S.make_hit_lists(sc, tiny)
+            cores = best_cpu_threads(lambda: port.multiply_forward(sc, tiny, thits))
             t0 = time.time()
             ref = port.multiply_forward(sc, sub, shits)
             dt = time.time() - t0

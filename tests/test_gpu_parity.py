@@ -215,3 +215,25 @@ def test_empty_hit_list_and_single_person():
     torch.cuda.synchronize()
     for k in ("rgb_values", "normal_values", "acc_map", "acc_person_list"):
         assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < 1e-4, k
+
+
+@pytest.mark.parametrize("P,Sn,R", [(3, 256, 40), (6, 32, 64)])
+def test_more_persons_and_samples(P, Sn, R):
+    """BASELINE configs 3 and 5 shapes at test size: 3 persons with 256 samples/ray (S/E/X = 256/512/128,
+    n = 385) and 6 persons; all rays hit every person (worst case of SURVEY.md §8d)."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    sc = S.make_scene(P=P, S=Sn, seed=42)
+    inp = S.make_rays(sc, R, seed=9, region="boxes")
+    hits = S.make_hit_lists(sc, inp, all_hit=True)
+    st = {}
+    ref = port.multiply_forward(sc, inp, hits, stats=st)
+    o = engine.Renderer(sc).render(inp, hits, debug=True)
+    torch.cuda.synchronize()
+    assert list(o["trips"].cpu().numpy()) == list(st["trips"])
+    assert o["acc_person_list"].shape == (R, P)
+    tol = 1e-4 if Sn >= 64 else 5e-4
+    for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
+        assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < tol, k
