@@ -150,6 +150,33 @@ int mp_camera_rays(const float* uv /*[R,2]*/, const float* pose /*[4,4]*/, const
 int mp_sphere_intersections(const float* cam_loc, const float* ray_dirs, int R, float r,
                             float* near_far /*[R,2]*/, int* status_flag, void* stream);
 
+/* Ray / box culling (replaces the host-side trimesh ray/triangle test on the x1.2 oriented box,
+ * multiply.py:208-214, :256-263): box = centre + half extents (host doubles) + optional 3x3 rotation (device
+ * doubles, rows = box axes, NULL = axis aligned).  idx_out [R] receives the hit ray ids in ascending order,
+ * count_dev their number.  An empty result is the caller's to replace by ray 0 (multiply.py:262-263). */
+int mp_ray_box_hits(const float* cam_loc, const float* ray_dirs, int R, const double* center_host,
+                    const double* half_extent_host, const double* rot_dev, int64_t* idx_out, int* count_dev,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SMPL server: SMPLServer.forward (lib/model/smpl.py:50-95) -> SMPL.forward (lib/smpl/body_models.py:278-364)
+ * -> lbs (lib/smpl/lbs.py:136-229).  Model arrays are the ones the SMPL pkl provides (device pointers, kept by
+ * reference); parents is a host array of 24 ints.  The canonical pose of smpl.py:35-47 is evaluated at creation.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mp_smpl mp_smpl_t;
+size_t mp_smpl_bytes(int V);
+int mp_smpl_create(const float* v_template /*[V,3]*/, const float* shapedirs /*[V,3,10]*/,
+                   const float* posedirs /*[207,V*3]*/, const float* J_regressor /*[24,V]*/,
+                   const int* parents_host /*[24]*/, const float* lbs_weights /*[V,24]*/, int V,
+                   const float* betas_canonical /*[10] device or NULL*/, void* storage, size_t storage_bytes,
+                   mp_smpl_t** out, void* stream);
+void mp_smpl_free(mp_smpl_t* s);
+/* SMPLServer.verts_c [V,3] and tfs_c_inv [24,4,4] (either may be NULL) */
+int mp_smpl_canonical(mp_smpl_t* s, float* verts_c, float* tfs_c_inv, void* stream);
+/* scale [1], transl [3], thetas [72], betas [10] (device) -> smpl_verts [V,3], smpl_tfs [24,4,4] */
+int mp_smpl_forward(mp_smpl_t* s, const float* scale, const float* transl, const float* thetas, const float* betas,
+                    int absolute, float* smpl_verts, float* smpl_tfs, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * sampler: ErrorBoundSampler (lib/model/ray_sampler.py:45-230), eval mode
  * ---------------------------------------------------------------------------------------- */

@@ -95,6 +95,12 @@ SIGNATURES = {
     "mp_laplace_density": (_I, [_VP, _I, _F, _VP, _VP]),
     "mp_camera_rays": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_sphere_intersections": (_I, [_VP, _VP, _I, _F, _VP, _VP, _VP]),
+    "mp_ray_box_hits": (_I, [_VP, _VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _VP, _VP, _VP, _VP]),
+    "mp_smpl_bytes": (_SZ, [_I]),
+    "mp_smpl_create": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_int), _VP, _I, _VP, _VP, _SZ, C.POINTER(_VP), _VP]),
+    "mp_smpl_free": (None, [_VP]),
+    "mp_smpl_canonical": (_I, [_VP, _VP, _VP, _VP]),
+    "mp_smpl_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_sampler_workspace_bytes": (_SZ, [C.POINTER(SamplerCfg), _I]),
     "mp_sample_rays": (_I, [C.POINTER(SamplerCfg), _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mp_sdf_with_deformer": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -19,7 +19,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 # reference-semantics kernels: keep a*a + b*b as two roundings (see sampler.cu header)
 NO_FMAD = {"sampler.cu", "composite.cu", "rays.cu", "background.cu", "deform.cu"}
 SOURCES = ["host_util.cu", "rays.cu", "deform.cu", "mlp_pack.cu", "mlp_simt.cu", "mlp_tc.cu", "sampler.cu",
-           "composite.cu", "background.cu", "render.cu"]
+           "composite.cu", "background.cu", "render.cu", "smpl.cu"]
 
 
 def _nvcc():

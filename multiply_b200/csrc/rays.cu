@@ -60,6 +60,61 @@ __global__ void sphere_kernel(const float* __restrict__ cam, const float* __rest
   nf[2 * i + 1] = tf;
 }
 
+// Ray / oriented-box culling (replaces the host-side trimesh RayMeshIntersector of multiply.py:208-214, :256-263).
+// Slab test in the box frame, fp64 like the host code it replaces; one CTA compacts the hit ray ids IN ORDER
+// (the reference sorts them, :258-259) with ballot + block scan, so no separate sort is needed.
+__global__ void __launch_bounds__(1024) ray_box_hits_kernel(const float* __restrict__ cam, const float* __restrict__ dirs,
+                                                            int R, double cx, double cy, double cz, double hx, double hy,
+                                                            double hz, const double* __restrict__ rot,
+                                                            int64_t* __restrict__ idx_out, int* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  double Rm[9];
+  for (int k = 0; k < 9; ++k) Rm[k] = rot ? rot[k] : ((k % 4 == 0) ? 1.0 : 0.0);
+  for (int r0 = 0; r0 < R; r0 += blockDim.x) {
+    int r = r0 + tid;
+    bool hit = false;
+    if (r < R) {
+      double o[3] = {(double)cam[3 * r] - cx, (double)cam[3 * r + 1] - cy, (double)cam[3 * r + 2] - cz};
+      double d[3] = {(double)dirs[3 * r], (double)dirs[3 * r + 1], (double)dirs[3 * r + 2]};
+      double h[3] = {hx, hy, hz};
+      double tmin = -1e300, tmax = 1e300;
+      for (int a = 0; a < 3; ++a) {
+        double oa = Rm[3 * a] * o[0] + Rm[3 * a + 1] * o[1] + Rm[3 * a + 2] * o[2];
+        double da = Rm[3 * a] * d[0] + Rm[3 * a + 1] * d[1] + Rm[3 * a + 2] * d[2];
+        if (fabs(da) < 1e-12) da = 1e-12;
+        double inv = 1.0 / da;
+        double t1 = (-h[a] - oa) * inv, t2 = (h[a] - oa) * inv;
+        tmin = fmax(tmin, fmin(t1, t2));
+        tmax = fmin(tmax, fmax(t1, t2));
+      }
+      hit = tmax >= fmax(tmin, 0.0);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane];
+      int incl = v;
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o2);
+        if (lane >= o2) incl += t;
+      }
+      s_warp[lane] = incl - v;          // exclusive prefix of the warp counts
+      if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    if (hit) idx_out[s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u))] = r;
+    __syncthreads();
+    if (tid == 0) s_base += s_total;
+    __syncthreads();
+  }
+  if (tid == 0 && count) *count = s_base;
+}
+
 __global__ void density_kernel(const float* __restrict__ sdf, int N, float beta, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) out[i] = laplace_density(sdf[i], beta);
@@ -83,6 +138,20 @@ int mp_sphere_intersections(const float* cam_loc, const float* ray_dirs, int R, 
   if (R <= 0) return 0;
   mp::sphere_kernel<<<mp::div_up(R, 256), 256, 0, (cudaStream_t)stream>>>(cam_loc, ray_dirs, R, r, near_far,
                                                                           status_flag);
+  MP_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_ray_box_hits(const float* cam_loc, const float* ray_dirs, int R, const double* center_host,
+                    const double* half_extent_host, const double* rot_dev, int64_t* idx_out, int* count_dev,
+                    void* stream) {
+  MP_REQUIRE(cam_loc && ray_dirs && center_host && half_extent_host && idx_out && count_dev,
+             "mp_ray_box_hits: null argument");
+  if (R <= 0) return 0;
+  mp::ray_box_hits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cam_loc, ray_dirs, R, center_host[0], center_host[1],
+                                                               center_host[2], half_extent_host[0],
+                                                               half_extent_host[1], half_extent_host[2], rot_dev,
+                                                               idx_out, count_dev);
   MP_LAUNCH_CHECK();
   return 0;
 }

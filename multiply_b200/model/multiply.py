@@ -113,12 +113,15 @@ class Multiply(nn.Module):
             r.bg.set_cond(frame.detach())
         hits = input.get("index_ray_box_list")
         if hits is None:
-            dirs, cam = rend_util.get_camera_params_host(input["uv"].detach().cpu(), input["pose"].detach().cpu(),
-                                                         input["intrinsics"].detach().cpu())
+            # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2, on the device
+            dirs, cam = rend_util.get_camera_params(input["uv"], input["pose"], input["intrinsics"])
+            dirs = dirs[0]
+            cam = cam.expand(dirs.shape[0], 3).contiguous()
             hits = []
             for i in range(P):
-                c, h = S.person_box(dict(verts_p=persons[i]["verts_p"].detach().cpu()))
-                hits.append(S.ray_box_hits(cam, dirs, c, h))
+                v = persons[i]["verts_p"]
+                lo, hi = v.min(0)[0], v.max(0)[0]
+                hits.append(engine.ray_box_hits(cam, dirs, ((lo + hi) / 2).tolist(), ((hi - lo) / 2 * 1.2).tolist()))
         bg_saved = r.bg
         if frame is None:
             r.bg = None                                                    # white background, multiply.py:540-541

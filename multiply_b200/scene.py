@@ -343,6 +343,25 @@ def make_hit_lists(scene, inputs, all_hit=False):
     return out
 
 
+def make_smpl_model(seed=300):
+    """Synthetic stand-in for the licence-gated SMPL pkl: the arrays lib/smpl/body_models.py:SMPL registers
+    (v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights), with SMPL's shapes."""
+    rng = np.random.RandomState(seed)
+    verts_t, W = make_body(100)
+    V = verts_t.shape[0]
+    shapedirs = 0.01 * rng.randn(V, 3, 10)
+    posedirs = 0.004 * rng.randn(207, V * 3)
+    Jr = np.zeros((24, V))
+    for j in range(24):
+        d = np.linalg.norm(verts_t - _J[j], axis=1)
+        idx = np.argsort(d)[:64]
+        w = np.exp(-(d[idx] / 0.08) ** 2) + 1e-6
+        Jr[j, idx] = w / w.sum()
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.float32)))
+    return dict(v_template=f32(verts_t), shapedirs=f32(shapedirs), posedirs=f32(posedirs), J_regressor=f32(Jr),
+                parents=torch.tensor(PARENTS, dtype=torch.int64), lbs_weights=f32(W))
+
+
 class SyntheticSMPLServer:
     """Offline stand-in for lib/model/smpl.py:SMPLServer (needs the licence-gated SMPL pkl): same call
     signature and output keys; the body is the capsule model above.  ``forward`` ignores betas (the

@@ -236,6 +236,14 @@ def main():
     xd = m.deformer_list[0].forward_skinning(xc[None], None, p0["tfs"][None])[0]
     save("deformer", pts=pts, x_c=xc, outlier=outl, x_d=xd)
 
+    # ---- SMPL linear blend skinning: the reference's own lib/smpl/lbs.py on a synthetic SMPL-shaped model ----
+    sm = S.make_smpl_model(300)
+    betas = 0.5 * torch.randn(1, 10, generator=g)
+    pose = 0.3 * torch.randn(1, 72, generator=g)
+    verts, _, _, _, A = ref.lbs.lbs(betas, pose, sm["v_template"][None], sm["shapedirs"], sm["posedirs"],
+                                    sm["J_regressor"], sm["parents"], sm["lbs_weights"], dtype=torch.float32)
+    save("smpl_lbs", betas=betas, pose=pose, verts=verts[0], A=A[0])
+
     # ---- sampler + full forward -----------------------------------------------------
     for name, Sn, R, region in (("forward_S64_R48", 64, 48, "boxes"), ("forward_S16_R96", 16, 96, "image")):
         sc = S.make_scene(P=2, S=Sn, seed=42)

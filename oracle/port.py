@@ -237,6 +237,80 @@ def sdf_func_with_smpl_deformer(x, person, cfg, chunk=65536):
 
 
 # --------------------------------------------------------------------------------------
+# SMPL server (lib/model/smpl.py:50-95 -> lib/smpl/body_models.py:278-364 -> lib/smpl/lbs.py:136-229)
+# --------------------------------------------------------------------------------------
+
+
+def batch_rodrigues(rot_vecs):
+    """lib/smpl/lbs.py:276-307."""
+    n = rot_vecs.shape[0]
+    angle = torch.norm(rot_vecs + 1e-8, dim=1, keepdim=True)
+    rot_dir = rot_vecs / angle
+    cos = torch.unsqueeze(torch.cos(angle), dim=1)
+    sin = torch.unsqueeze(torch.sin(angle), dim=1)
+    rx, ry, rz = torch.split(rot_dir, 1, dim=1)
+    zeros = torch.zeros((n, 1))
+    K = torch.cat([zeros, -rz, ry, rz, zeros, -rx, -ry, rx, zeros], dim=1).view((n, 3, 3))
+    ident = torch.eye(3).unsqueeze(dim=0)
+    return ident + sin * K + (1 - cos) * torch.bmm(K, K)
+
+
+def batch_rigid_transform(rot_mats, joints, parents):
+    """lib/smpl/lbs.py:323-378 (batch 1): returns (posed_joints [J,3], rel_transforms A [J,4,4])."""
+    J = joints.shape[0]
+    rel = joints.clone()
+    rel[1:] = rel[1:] - joints[parents[1:]]
+    T = torch.zeros(J, 4, 4)
+    T[:, :3, :3] = rot_mats
+    T[:, :3, 3] = rel
+    T[:, 3, 3] = 1
+    chain = [T[0]]
+    for i in range(1, J):
+        chain.append(torch.matmul(chain[int(parents[i])], T[i]))
+    G = torch.stack(chain, dim=0)
+    jh = F.pad(joints, [0, 1]).unsqueeze(-1)
+    A = G - F.pad(torch.matmul(G, jh), [3, 0, 0, 0, 0, 0])
+    return G[:, :3, 3], A
+
+
+def lbs(betas, pose, model):
+    """lib/smpl/lbs.py:136-229 (batch 1, pose2rot, pose_blend): betas [10], pose [72] ->
+    (verts [V,3], A [24,4,4])."""
+    v_shaped = model["v_template"] + torch.einsum('l,mkl->mk', betas, model["shapedirs"])
+    J = torch.einsum('ik,ji->jk', v_shaped, model["J_regressor"])
+    rot = batch_rodrigues(pose.view(-1, 3))
+    pose_feature = (rot[1:] - torch.eye(3)).reshape(1, -1)
+    v_posed = v_shaped + torch.matmul(pose_feature, model["posedirs"]).view(-1, 3)
+    _, A = batch_rigid_transform(rot, J, model["parents"])
+    T = torch.matmul(model["lbs_weights"], A.view(24, 16)).view(-1, 4, 4)
+    vh = torch.cat([v_posed, torch.ones(v_posed.shape[0], 1)], dim=1)
+    verts = torch.matmul(T, vh.unsqueeze(-1))[:, :3, 0]
+    return verts, A
+
+
+def smpl_server_forward(model, tfs_c_inv, scale, transl, thetas, betas, absolute=False):
+    """SMPLServer.forward, lib/model/smpl.py:50-95: scale [1], transl [3], thetas [72], betas [10] ->
+    dict(smpl_verts [V,3], smpl_tfs [24,4,4])."""
+    verts, A = lbs(betas, thetas, model)
+    out_verts = verts * scale + transl * scale
+    tf = A.clone()
+    tf[:, :3, :] = tf[:, :3, :] * scale
+    tf[:, :3, 3] = tf[:, :3, 3] + transl * scale
+    if not absolute:
+        tf = torch.einsum('nij,njk->nik', tf, tfs_c_inv)
+    return {"smpl_verts": out_verts, "smpl_tfs": tf}
+
+
+def smpl_canonical_tfs_inv(model, betas):
+    """SMPLServer.__init__, smpl.py:35-47: canonical pose (hips +-pi/6 about z), absolute transforms, inverted."""
+    th = torch.zeros(72)
+    th[5] = np.pi / 6
+    th[8] = -np.pi / 6
+    out = smpl_server_forward(model, None, torch.ones(1), torch.zeros(3), th, betas, absolute=True)
+    return out["smpl_tfs"].inverse(), out["smpl_verts"]
+
+
+# --------------------------------------------------------------------------------------
 # rays (lib/utils/rend_util.py)
 # --------------------------------------------------------------------------------------
 

@@ -110,3 +110,39 @@ def test_operator_mirrors():
     xr, orf = port.deform_inverse(pts, p0)
     assert bool((outl.cpu() == orf).all()) and float((xc.cpu() - xr).abs().max()) < 1e-5
     assert net(x[:0].cuda(), {"smpl": p0["cond"].cuda()}).shape[1] == 0      # zero-size early return
+
+
+def test_smpl_server_and_culling(golden_dir):
+    """SMPLServer (lbs) against the reference's lbs.py output (golden) and the oracle's SMPLServer.forward;
+    GPU ray/box culling against the host slab test."""
+    import os
+    from multiply_b200 import engine
+    from multiply_b200.model.smpl import SMPLServer
+    from multiply_b200.model import rend_util
+    from oracle import port
+    g = np.load(os.path.join(golden_dir, "smpl_lbs.npz"))
+    sm = S.make_smpl_model(300)
+    srv = SMPLServer(model=sm)
+    betas, pose = torch.from_numpy(g["betas"]), torch.from_numpy(g["pose"])
+    out = srv(torch.ones(1), torch.zeros(1, 3), pose, betas, absolute=True)
+    torch.cuda.synchronize()
+    assert float(np.abs(out["smpl_verts"][0].cpu().numpy() - g["verts"]).max()) < 5e-6
+    assert float(np.abs(out["smpl_tfs"][0].cpu().numpy() - g["A"]).max()) < 5e-6
+    # SMPLServer.forward with scale / translation / canonical inverse vs the oracle (smpl.py:50-95)
+    tinv, vc = port.smpl_canonical_tfs_inv(sm, torch.zeros(10))
+    assert float((srv.verts_c[0].cpu() - vc).abs().max()) < 5e-6
+    assert float((srv.tfs_c_inv.cpu() - tinv).abs().max()) < 5e-5
+    ref = port.smpl_server_forward(sm, tinv, torch.tensor([0.5]), torch.tensor([0.3, 0.1, -0.2]), pose[0], betas[0])
+    out = srv(torch.tensor([0.5]), torch.tensor([[0.3, 0.1, -0.2]]), pose, betas)
+    torch.cuda.synchronize()
+    assert float((out["smpl_verts"][0].cpu() - ref["smpl_verts"]).abs().max()) < 5e-6
+    assert float((out["smpl_tfs"][0].cpu() - ref["smpl_tfs"]).abs().max()) < 5e-5
+    # culling
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 5000, seed=3, region="image")
+    dirs, cam = rend_util.get_camera_params_host(inp["uv"], inp["pose"], inp["intrinsics"])
+    for person in sc["persons"]:
+        c, h = S.person_box(person)
+        ref_hits = S.ray_box_hits(cam, dirs, c, h)
+        got = engine.ray_box_hits(cam.cuda(), dirs.cuda(), c.tolist(), h.tolist())
+        assert torch.equal(got.cpu(), ref_hits)

@@ -95,3 +95,12 @@ def test_forward(golden_dir, name, Sn, R, region):
     for p in range(2):
         assert np.abs(o["_z_vals"][p].numpy() - g[f"z_vals_{p}"]).max() < 2e-4
         assert np.abs(o["_sdf"][p].numpy() - g[f"sdf_{p}"]).max() < 1e-4
+
+
+def test_smpl_lbs(golden_dir):
+    """oracle/port.lbs against the reference's lib/smpl/lbs.py:lbs (run unmodified by gen_golden)."""
+    g = _g(golden_dir, "smpl_lbs")
+    sm = S.make_smpl_model(300)
+    verts, A = port.lbs(torch.from_numpy(g["betas"])[0], torch.from_numpy(g["pose"])[0], sm)
+    assert np.abs(verts.numpy() - g["verts"]).max() < 2e-6
+    assert np.abs(A.numpy() - g["A"]).max() < 2e-6
