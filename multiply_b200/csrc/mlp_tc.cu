@@ -35,7 +35,8 @@ enum {
   F_FINAL_GRAD = 32,   // reverse sweep end: d sdf / d x -> normal ; then reload the features into A
   F_EXTRA_IN = 64,     // colour layer 0: add W0[:, :n_extra] . extra inputs
   F_RGB_OUT = 128,     // last colour layer: rgb = sigmoid(h . Wrgb^T + b)
-  F_FEAT_OUT = 256     // write the fp32 features to feat_out (operator API)
+  F_FEAT_OUT = 256,    // write the fp32 features to feat_out (operator API)
+  F_STASH_FEAT = 512   // park the feature chunks in scratch (they return as the colour net's input after the reverse sweep)
 };
 constexpr int kMaxSteps = 24;
 constexpr int kSlotBytes = 32768;          // 256 rows x 64 fp16
@@ -208,20 +209,38 @@ template <int N>
 __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // softplus(beta=100, threshold=20) and its derivative (networks.py:85)
-// Branch-free so that the 32 elements of a chunk pipeline through the MUFU unit (a per-element branch
-// serialises them: measured 5x slower, profiles/r1_tc_kernel.md).
+// Branch-free so that the elements of a chunk pipeline through the MUFU unit (a per-element branch serialises
+// them: measured 5x slower).  Raw MUFU approximations (ex2 / lg2 / rcp .approx.ftz) without the
+// denormal fix-ups of __expf/__logf: arguments are clamped to [-inf, 20*log2(e)] and 1+u >= 1, results only need
+// ~1e-7 absolute accuracy (softplus = log1p(exp(100 z))/100).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float softplus_fast(float z) {
-  float t = 100.f * z;
-  float u = __expf(fminf(t, 20.f));
-  float y = __logf(1.f + u) * 0.01f;
-  return t > 20.f ? z : y;
+  float t = z * 144.26950408889634f;                 // 100 z log2(e)
+  float u = ex2_approx(fminf(t, 28.853900817779268f));
+  float y = lg2_approx(1.f + u) * 0.0069314718055994531f;   // ln2 / 100
+  return t > 28.853900817779268f ? z : y;
 }
 __device__ __forceinline__ void softplus_fast_grad(float z, float& y, float& d) {
-  float t = 100.f * z;
-  float u = __expf(fminf(t, 20.f));
-  float r = __fdividef(1.f, 1.f + u);
-  float ys = __logf(1.f + u) * 0.01f;
-  bool big = t > 20.f;
+  float t = z * 144.26950408889634f;
+  float u = ex2_approx(fminf(t, 28.853900817779268f));
+  float w = 1.f + u;
+  float r = rcp_approx(w);
+  float ys = lg2_approx(w) * 0.0069314718055994531f;
+  bool big = t > 28.853900817779268f;
   y = big ? z : ys;
   d = big ? 1.f : u * r;
 }
@@ -571,7 +590,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
 #pragma unroll
             for (int j = 0; j < CW; j += 8) store_a8(A, row, c + j, v + j);
-            if (st.epi == EPI_FEAT && (s + 1 < P.nsteps)) {
+            if (st.flags & F_STASH_FEAT) {
               // stash the feature chunks (they come back as the colour net's input)
 #pragma unroll
               for (int j = 0; j < CW; j += 8) {
@@ -1076,7 +1095,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
           if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
 #pragma unroll
             for (int j = 0; j < CW; j += 8) store_out8(to_tmem, A, t_row, row, c + j, v + j);
-            if (st.epi == EPI_FEAT && (s + 1 < P.nsteps)) {
+            if (st.flags & F_STASH_FEAT) {
               // stash the feature chunks (they come back as the colour net's input)
 #pragma unroll
               for (int j = 0; j < CW; j += 8) {
@@ -1427,9 +1446,10 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
     P.nsteps = s;
     P.slots_per_tile = c.nslots;
     tb->full_prog = P;
+    for (int i = 0; i < 8; ++i) tb->full_prog.step[i].flags &= ~F_SAVE_SIG;   // no reverse sweep in the background
   }
   if (fg_chain) {
-    P.step[s - 1].flags |= F_SEED_BWD;
+    P.step[s - 1].flags |= F_SEED_BWD | F_STASH_FEAT;
     // ---- reverse sweep B7..B1: g_{l-1} = (g_l * sigma'_l) . W_l ----
     for (int l = 7; l >= 1; --l) {
       int in = f.imp_in[l], out = f.imp_out[l];
@@ -1532,6 +1552,14 @@ int prof_read(double* ms, long long* launches, double* points, int reset) {
 
 static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cudaStream_t st, int kind) {
   int grid = sm_count();
+  {
+    static int grid_override = -1;
+    if (grid_override < 0) {
+      const char* eg = getenv("MP_TC_GRID");     // experiment knob: number of persistent CTAs
+      grid_override = eg ? atoi(eg) : 0;
+    }
+    if (grid_override > 0 && grid_override < grid) grid = grid_override;
+  }
   int maxtiles = (io.cap + 127) / 128;
   if (grid > maxtiles) grid = maxtiles;
   if (grid < 1) return 0;
