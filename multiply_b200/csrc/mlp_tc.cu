@@ -78,6 +78,7 @@ struct TcIO {
   float* nrm_out;        // [slots,3]
   float* grad_out;       // [cap,3] dense or nullptr
   float* feat_out;       // [cap,256] dense or nullptr
+  int variant;           // timing experiments on the v2 kernel (MP_TC_VARIANT): 1 = operand always in smem, 2 = no half hand-over
   char* scratch;         // per-CTA scratch
   size_t scratch_per_cta;
 };
@@ -849,7 +850,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int s = 0; s < P.nsteps; ++s) {
           const int nk = P.step[s].nk;
-          const bool from_tmem = (s & 1) != 0;
+          const bool from_tmem = ((s & 1) != 0) && !(io.variant & 1);
           for (int h = 0; h < 2; ++h) {
             const uint32_t dcol = tmem + (uint32_t)(128 * h);
             uint32_t acc = 0;
@@ -959,8 +960,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
         const float isc = P.inv_scale[s];
-        const bool to_tmem = ((s + 1) & 1) != 0;         // where the next layer reads its operand from
-        const bool late = (st.flags & (F_SEED_BWD | F_FINAL_GRAD)) != 0;   // tails rewrite the operand
+        const bool to_tmem = (((s + 1) & 1) != 0) && !(io.variant & 1);   // where the next layer reads its operand from
+        const bool late = ((st.flags & (F_SEED_BWD | F_FINAL_GRAD)) != 0) || (io.variant & 2);   // tails rewrite the operand
         if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
         float va[CW];
@@ -1567,6 +1568,14 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
              ws_bytes, (size_t)grid * kScratchPerCta);
   io.scratch = (char*)ws;
   io.scratch_per_cta = kScratchPerCta;
+  {
+    static int variant = -1;
+    if (variant < 0) {
+      const char* ev = getenv("MP_TC_VARIANT");
+      variant = ev ? atoi(ev) : 0;
+    }
+    io.variant = variant;
+  }
   static bool attr_set = false;
   static int nw = 16;
   static int v2 = 0;   // overlapped TS-mode variant: correct (all parity tests) but measured 6 % slower, see profiles/
