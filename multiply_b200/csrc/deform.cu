@@ -190,7 +190,10 @@ __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* _
   bool inside = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.dim[0] && cy < g.dim[1] && cz < g.dim[2];
   float hh = g.h * 0.999f;
   if (!full_scan_if_unsure) {
-    // outlier classification only: any vertex within the 0.1 radius lies in the 3x3x3 block (cell >= 0.1001)
+    // outlier classification only: any vertex within the 0.1 radius lies in the 3x3x3 block (cell >= 0.1001).
+    // The grid carries two empty border cells, so a query whose cell is not in [1, dim-2] on some axis has
+    // no vertex in its block at all: the common case for samples far from the body.
+    if (cx < 1 || cy < 1 || cz < 1 || cx > g.dim[0] - 2 || cy > g.dim[1] - 2 || cz > g.dim[2] - 2) return;
     scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
     return;
   }

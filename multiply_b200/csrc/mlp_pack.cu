@@ -10,6 +10,7 @@ namespace mp {
 
 int tc_pack(Field& f, Arena& a, cudaStream_t st);   // mlp_tc.cu
 size_t tc_pack_bytes();
+void tc_free(Field& f);
 
 // W_nat[o][i] = (g ? g[o] * v[o][i] / ||v[o]|| : v[o][i]) * scale ; one warp per output row
 __global__ void fold_kernel(const float* __restrict__ v, const float* __restrict__ g, int out, int in, float scale,
@@ -233,7 +234,10 @@ int mp_field_pack(const mp_implicit_desc_t* imp, const mp_render_desc_t* ren, in
   return 0;
 }
 
-void mp_field_free(mp_net_t* f) { delete f; }
+void mp_field_free(mp_net_t* f) {
+  if (f) mp::tc_free(f->f);
+  delete f;
+}
 
 int mp_field_set_cond(mp_net_t* h, const float* cond, void* stream) {
   using namespace mp;

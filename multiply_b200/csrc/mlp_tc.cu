@@ -426,12 +426,27 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       const int slot = valid ? (io.slot ? io.slot[pt] : pt) : 0;
       // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
       {
+        // positional embedding (embedders.py:8-34): the (frequency, axis) pairs of a row are split over its
+        // column-part threads, one sincosf each, parked in scratch (the `ge` region is free until the reverse
+        // sweep) so that the skip connection of layer 4 re-reads instead of recomputing them
+        const int npair = d * P.multires;
+        for (int pi = part; pi < npair; pi += NPART) {
+          int f = pi / d, a = pi - f * d;
+          float sn, cs;
+          sincosf(__fmul_rn(x[a], (float)(1 << f)), &sn, &cs);
+          ge[(size_t)(d + 2 * f * d + a) * 128 + row] = sn;
+          ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row] = cs;
+        }
+        if (part == 0)
+          for (int a = 0; a < d; ++a) ge[(size_t)a * 128 + row] = x[a];
+        __threadfence_block();
+        ep_bar<NEPI>();
         const int ncol = P.step[0].nk * 64;
         const int c0 = part * (ncol / NPART), c1 = c0 + ncol / NPART;
         for (int c = c0; c < c1; c += 8) {
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? embed_elem(x, d, c + j) : 0.f;
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? ge[(size_t)(c + j) * 128 + row] : 0.f;
           store_a8(A, row, c, v);
         }
         fence_async_smem();
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             if ((st.flags & F_INJECT_EMB) && c + CW > P.inj_col) {
 #pragma unroll
               for (int j = 0; j < CW; ++j)
-                if (c + j >= P.inj_col) v[j] = embed_elem(x, d, c + j - P.inj_col);
+                if (c + j >= P.inj_col) v[j] = ge[(size_t)(c + j - P.inj_col) * 128 + row];
             }
             if (st.flags & F_SDF_DOT) {
 #pragma unroll
@@ -930,12 +945,27 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
       const int slot = valid ? (io.slot ? io.slot[pt] : pt) : 0;
       // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
       {
+        // positional embedding (embedders.py:8-34): the (frequency, axis) pairs of a row are split over its
+        // column-part threads, one sincosf each, parked in scratch (the `ge` region is free until the reverse
+        // sweep) so that the skip connection of layer 4 re-reads instead of recomputing them
+        const int npair = d * P.multires;
+        for (int pi = part; pi < npair; pi += NPART) {
+          int f = pi / d, a = pi - f * d;
+          float sn, cs;
+          sincosf(__fmul_rn(x[a], (float)(1 << f)), &sn, &cs);
+          ge[(size_t)(d + 2 * f * d + a) * 128 + row] = sn;
+          ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row] = cs;
+        }
+        if (part == 0)
+          for (int a = 0; a < d; ++a) ge[(size_t)a * 128 + row] = x[a];
+        __threadfence_block();
+        ep_bar<NEPI>();
         const int ncol = P.step[0].nk * 64;
         const int c0 = part * (ncol / NPART), c1 = c0 + ncol / NPART;
         for (int c = c0; c < c1; c += 8) {
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? embed_elem(x, d, c + j) : 0.f;
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? ge[(size_t)(c + j) * 128 + row] : 0.f;
           store_a8(A, row, c, v);
         }
         fence_async_smem();
@@ -999,7 +1029,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
             if ((st.flags & F_INJECT_EMB) && c + CW > P.inj_col) {
 #pragma unroll
               for (int j = 0; j < CW; ++j)
-                if (c + j >= P.inj_col) v[j] = embed_elem(x, d, c + j - P.inj_col);
+                if (c + j >= P.inj_col) v[j] = ge[(size_t)(c + j - P.inj_col) * 128 + row];
             }
             if (st.flags & F_SDF_DOT) {
 #pragma unroll
@@ -1354,6 +1384,11 @@ static void pack_layer(PackCtx& c, int step, const float* W, int ld, int transpo
   }
   copy_strided_kernel<<<1, 1, 0, c.st>>>(c.scales + 2 * step + 1, 1, 1, c.inv_scale + step);
   g_launches++;
+}
+
+void tc_free(Field& f) {
+  delete (TcBlob*)f.tc;
+  f.tc = nullptr;
 }
 
 int tc_pack(Field& f, Arena& a, cudaStream_t st) {

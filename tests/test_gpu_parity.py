@@ -237,3 +237,51 @@ def test_more_persons_and_samples(P, Sn, R):
     tol = 1e-4 if Sn >= 64 else 5e-4
     for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
         assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < tol, k
+
+
+def test_edge_cases_single_ray_and_no_hits():
+    """R = 1, and a batch in which no ray hits any box (every hit list empty -> ray 0, multiply.py:262-263):
+    the outputs equal the oracle's and untouched rays are pure background (acc 0, bg_T 1)."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    one = S.make_rays(sc, 1, seed=2, region="boxes")
+    hits = S.make_hit_lists(sc, one)
+    ref = port.multiply_forward(sc, one, hits)
+    o = engine.Renderer(sc).render(one, hits)
+    torch.cuda.synchronize()
+    assert _maxabs(o["rgb_values"].cpu().numpy(), ref["rgb_values"].numpy()) < 1e-4
+    # rays in an image corner miss both boxes
+    K, pose = S.make_camera()
+    uv = torch.rand(1, 33, 2, generator=torch.Generator().manual_seed(4)) * 6.0
+    inp = dict(uv=uv, pose=pose, intrinsics=K)
+    hits = S.make_hit_lists(sc, inp)
+    assert all(h.numel() == 0 for h in hits)
+    ref = port.multiply_forward(sc, inp, hits)
+    o = engine.Renderer(sc).render(inp, hits, debug=True)
+    torch.cuda.synchronize()
+    for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
+        assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < 1e-4, k
+    assert float(o["acc_map"][1:].abs().max()) == 0.0 and float((o["bg_T"][1:] - 1).abs().max()) == 0.0
+
+
+def test_abi_reports_errors():
+    """Error convention of the C ABI: negative status + mp_last_error(), nothing thrown, nothing written."""
+    import ctypes as C
+    from multiply_b200 import _lib as L, engine
+    lib = L.lib()
+    sc = S.make_scene(P=1, S=16, seed=42)
+    r = engine.Renderer(sc)
+    c = engine.sampler_cfg(sc["cfg"], 0.1)
+    d = torch.zeros(8, 3, device="cuda")
+    z = torch.zeros(8, 16 + 8 + 2, device="cuda")
+    tiny = torch.empty(64, dtype=torch.uint8, device="cuda")
+    rc = lib.mp_sample_rays(C.byref(c), r.bodies[0].handle, r.fields[0].handle, d.data_ptr(), d.data_ptr(), 8, z.data_ptr(),
+                            None, None, tiny.data_ptr(), tiny.numel(), L.stream_ptr())
+    assert rc != 0 and b"workspace too small" in lib.mp_last_error()
+    rc = lib.mp_sample_rays(C.byref(c), None, r.fields[0].handle, d.data_ptr(), d.data_ptr(), 8, z.data_ptr(), None, None,
+                            tiny.data_ptr(), tiny.numel(), L.stream_ptr())
+    assert rc != 0 and b"null argument" in lib.mp_last_error()
+    with pytest.raises(L.MpError):
+        L.check(rc, "mp_sample_rays")
