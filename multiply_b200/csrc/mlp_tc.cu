@@ -469,6 +469,13 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
         const float isc = P.inv_scale[s];
+        // reverse-sweep steps: start fetching sigma' of the first chunk before blocking on the accumulator
+        float4 s4[G4];
+        const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
+        if (need_sig) {
+#pragma unroll
+          for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((cbeg >> 2) + g4)) * 128 + row];
+        }
         mbar_wait(d_full, df_ph);
         df_ph ^= 1;
         tc_fence_after();
@@ -476,12 +483,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
         float va[CW];
         auto process_chunk = [&](float* v, float* vnext, const int c) {
-          float4 s4[G4];
-          const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
-          if (need_sig) {   // issue the sigma' loads before waiting on TMEM: they are the long-latency part
-#pragma unroll
-            for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
-          }
           tmem_wait<CW>(v);
           if (st.epi == EPI_SOFTPLUS) {
             float4 b4[G4];
@@ -564,6 +565,11 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 v[4 * g4 + 2] *= isc * s4[g4].z;
                 v[4 * g4 + 3] *= isc * s4[g4].w;
               }
+            }
+            if (need_sig && c + CW < cend) {   // next chunk's sigma' streams in behind the stores below
+#pragma unroll
+              for (int g4 = 0; g4 < G4; ++g4)
+                s4[g4] = sig[((size_t)st.sig * 64 + (((c + CW) >> 2) + g4)) * 128 + row];
             }
           } else {   // EPI_RELU
 #pragma unroll
