@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--engine", default=os.environ.get("MP_ENGINE", "tc"))
@@ -264,6 +264,12 @@ def main():
             all_flops += hits[p].numel() * (trips[p] * E * F_SDF + n * (F_SDF + B_SDF + F_RGB))
         all_flops += R * 32 * F_BG
         h2d = sum(v.numel() * v.element_size() for v in h_inp.values()) + sum(h.numel() * 8 for h in h_hits)
+        traffic = None
+        for tag in ("r2", "r1"):
+            tp = os.path.join(ROOT, "profiles", tag + "_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp))["tc_chain_kernel_dram_bytes_per_step"]
+                break
         line = {
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -274,7 +280,10 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                         "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
+                         "traffic_note": "DRAM bytes of the kernel's launches of one step (ncu capture, profiles/); achieved is "
+                                         "likewise aggregated over the step's launches.  Algorithmic bytes are ~6.6 MB of weights "
+                                         "per field; the excess is the sigma' scratch of the reverse sweep spilling out of L2",
                          "kernel": "tc_chain_kernel (fused SDF/grad/colour MLP chain)",
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "kernel_ms_per_step": mlp_ms / args.steps, "kernel_launches_per_step": n_l / args.steps,

@@ -60,6 +60,18 @@ with open(f"{out_dir}/{tag}_tc_kernel.md", "w") as f:
             if w in ix:
                 f.write(f"| {w} | {r[ix[w]]} | {units[ix[w]]} |\n")
         f.write("\n")
+    # DRAM traffic of the kernel over one step (the 8 captured launches = every non-trivial launch of a step;
+    # the 5 skipped leading launches are person 0's sampler trips: one 0.1 ms launch + 4 empty ones)
+    import json
+    tr = 0.0
+    for r in rr[2:]:
+        mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tr += float(r[ix["dram__bytes_read.sum"]]) * mult[units[ix["dram__bytes_read.sum"]]]
+        tr += float(r[ix["dram__bytes_write.sum"]]) * mult[units[ix["dram__bytes_write.sum"]]]
+    json.dump({"tc_chain_kernel_dram_bytes_per_step": tr, "launches_captured": len(rr) - 2,
+               "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s_tc_kernel.md" % tag},
+              open(f"{out_dir}/{tag}_traffic.json", "w"), indent=1)
+    f.write(f"DRAM traffic summed over these launches (one step): {tr / 1e9:.2f} GB\n\n")
     # stall reasons of the first big launch (source page)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", "::regex:tc_chain:1"],
                          capture_output=True, text=True).stdout
