@@ -296,7 +296,7 @@ def main():
             "sampler_trips": trips, "engine": args.engine,
         }
         # issued tensor FLOPs: every step of every tile is 3 MMAs of 128x256x(64*nk)
-        steps_nk = {0: 29, 1: 33, 2: 81, 3: 38}   # 64-wide K chunks per tile of each program (mlp_tc.cu:tc_pack)
+        steps_nk = {0: 29, 1: 33, 2: 77, 3: 34}   # 64-wide K chunks per tile of each program (mlp_tc.cu:tc_pack)
         issued = 0.0
         for k in range(4):
             tiles = pp[k] / 128.0

@@ -127,6 +127,8 @@ struct Field {
   float* ren_W0cond;               // [cdim][out0] : (W0[:, 6:14] @ lin_pose.W) for mode 0 ([69][out0]); W0[:,27:59]^T for mode 1 ([32][out0])
   float* ren_b0_base;              // [out0] : b0 + W0[:,6:14] @ lin_pose.b  (mode 0) ; b0 (mode 1)
   int ren_cond_dim;
+  float* ren_cb;                   // [out0] Wc0[:, feat] . b8[1:]  (colour layer 0 folded onto the feature layer)
+  float* ren_b0_fold;              // [out0] ren_b0_eff + ren_cb : bias of the folded layer (tcgen05 chains)
   // tcgen05 engine blobs (mlp_tc.cu); null until packed
   void* tc;
   char* storage;

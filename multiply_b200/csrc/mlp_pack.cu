@@ -65,6 +65,11 @@ __global__ void pose_fold_kernel(const float* __restrict__ W0, int in0, int out0
   }
 }
 
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = a[i] + b[i];
+}
+
 __global__ void copy_kernel(const float* __restrict__ s, float* __restrict__ d, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = s[i];
@@ -251,6 +256,10 @@ int mp_field_set_cond(mp_net_t* h, const float* cond, void* stream) {
   bias_fold_kernel<<<div_up(out0, 128), 128, 0, st>>>(f.ren_b0_base, f.ren_W0cond, cond, f.ren_cond_dim, out0,
                                                       f.ren_b0_eff);
   MP_LAUNCH_CHECK();
+  if (f.ren_b0_fold) {
+    add_vec_kernel<<<div_up(out0, 128), 128, 0, st>>>(f.ren_b0_eff, f.ren_cb, out0, f.ren_b0_fold);
+    MP_LAUNCH_CHECK();
+  }
   return 0;
 }
 }

@@ -49,6 +49,8 @@ struct TcStep {
   int sig;              // sigma' scratch layer (save: forward, load: reverse) or -1
   const float* bias;    // [256] or nullptr
   int ncols;            // output columns that carry data (the rest are padding)
+  int slot_off;         // first weight slot of this step in the blob
+  int sc;               // index of this layer's 2^-s in inv_scale[]
 };
 
 struct TcProgram {
@@ -350,13 +352,16 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const char* src = (const char*)P.blob;
-        for (int s = 0; s < P.slots_per_tile; ++s, ++it) {
-          int r = it % kRing;
-          uint32_t ph = (it / kRing) & 1;
-          mbar_wait(&empty[r], ph ^ 1);
-          mbar_expect_tx(&full[r], kSlotBytes);
-          bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)s * kSlotBytes, kSlotBytes, &full[r]);
+        for (int s = 0; s < P.nsteps; ++s) {
+          const char* src = (const char*)P.blob + (size_t)P.step[s].slot_off * kSlotBytes;
+          const int nslot = 2 * P.step[s].nk;
+          for (int j = 0; j < nslot; ++j, ++it) {
+            int r = it % kRing;
+            uint32_t ph = (it / kRing) & 1;
+            mbar_wait(&empty[r], ph ^ 1);
+            mbar_expect_tx(&full[r], kSlotBytes);
+            bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)j * kSlotBytes, kSlotBytes, &full[r]);
+          }
         }
       }
     }
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       }
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
-        const float isc = P.inv_scale[s];
+        const float isc = P.inv_scale[st.sc];
         // reverse-sweep steps: start fetching sigma' of the first chunk before blocking on the accumulator
         float4 s4[G4];
         const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
@@ -845,8 +850,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const char* src = (const char*)P.blob;
         for (int s = 0; s < P.nsteps; ++s) {
+          const char* src = (const char*)P.blob + (size_t)P.step[s].slot_off * kSlotBytes;
           const int nslot = 2 * P.step[s].nk;              // v1 slots of this step: (kc, hi|lo)
           for (int h = 0; h < 2; ++h) {
             for (int j = 0; j < nslot; ++j, ++it) {
@@ -858,7 +863,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
                        &full[r]);
             }
           }
-          src += (size_t)nslot * kSlotBytes;
         }
       }
     }
@@ -995,7 +999,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __gr
       }
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
-        const float isc = P.inv_scale[s];
+        const float isc = P.inv_scale[st.sc];
         const bool to_tmem = (((s + 1) & 1) != 0) && !(io.variant & 1);   // where the next layer reads its operand from
         const bool late = ((st.flags & (F_SEED_BWD | F_FINAL_GRAD)) != 0) || (io.variant & 2);   // tails rewrite the operand
         if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
@@ -1360,9 +1364,26 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, int lds, int nrow
   dst[i] = (c < ncols) ? src[(size_t)r * lds + c] : 0.f;
 }
 
+// M[n][k] = sum_j Wc[n][coff + j] * W8f[j][k]   (n < n_rows, k < 256; W8f = W8[1:], row stride ld8)
+// cb[n]   = sum_j Wc[n][coff + j] * b8f[j]
+__global__ void fold_mm_kernel(const float* __restrict__ Wc, int ldc, int coff, const float* __restrict__ W8f, int ld8,
+                               const float* __restrict__ b8f, int n_rows, float* __restrict__ M, float* __restrict__ cb) {
+  int k = blockIdx.x * 16 + threadIdx.x, n = blockIdx.y * 16 + threadIdx.y;
+  if (n >= n_rows || k >= 256) return;
+  const float* w = Wc + (size_t)n * ldc + coff;
+  double acc = 0.0;
+  for (int j = 0; j < 256; ++j) acc += (double)w[j] * (double)W8f[(size_t)j * ld8 + k];
+  M[(size_t)n * 256 + k] = (float)acc;
+  if (k == 0) {
+    double a2 = 0.0;
+    for (int j = 0; j < 256; ++j) a2 += (double)w[j] * (double)b8f[j];
+    cb[n] = (float)a2;
+  }
+}
+
 size_t tc_pack_bytes() {
   // sdf (58) + fwd (66) + full (162) slots ... share: full program contains fwd which contains sdf
-  return (size_t)170 * kSlotBytes + (1 << 16);
+  return (size_t)170 * kSlotBytes + (1 << 20);
 }
 
 struct PackCtx {
@@ -1370,14 +1391,19 @@ struct PackCtx {
   cudaStream_t st;
   uint8_t* blob;
   int nslots;
-  float* scales;      // [kMaxSteps][2] (scale, inv)
+  int nlayers;        // packed layers so far (index into scales / inv_scale)
+  float* scales;      // [kMaxLayers][2] (scale, inv)
   float* inv_scale;   // [kMaxSteps]
   int rc;
 };
 
-static void pack_layer(PackCtx& c, int step, const float* W, int ld, int transposed, int n_off, int k_off,
-                       int n_valid, int k_valid, int nk, int total_elems) {
-  if (c.rc) return;
+static int pack_layer(PackCtx& c, TcStep& stp, const float* W, int ld, int transposed, int n_off, int k_off,
+                      int n_valid, int k_valid, int nk, int total_elems) {
+  const int first = c.nslots;
+  const int step = c.nlayers++;
+  stp.slot_off = first;
+  stp.sc = step;
+  if (c.rc) return first;
   absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step);
   g_launches++;
   for (int kc = 0; kc < nk; ++kc) {
@@ -1390,6 +1416,7 @@ static void pack_layer(PackCtx& c, int step, const float* W, int ld, int transpo
   }
   copy_strided_kernel<<<1, 1, 0, c.st>>>(c.scales + 2 * step + 1, 1, 1, c.inv_scale + step);
   g_launches++;
+  return first;
 }
 
 void tc_free(Field& f) {
@@ -1407,9 +1434,10 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   c.st = st;
   c.rc = 0;
   c.nslots = 0;
+  c.nlayers = 0;
   c.blob = (uint8_t*)a.take<uint4>((size_t)170 * kSlotBytes / 16);
-  c.scales = a.take<float>(2 * kMaxSteps);
-  c.inv_scale = a.take<float>(kMaxSteps);
+  c.scales = a.take<float>(2 * 32);
+  c.inv_scale = a.take<float>(32);
   float* w8row = a.take<float>(256);
   float* W0x = a.take<float>(32 * 256);
   float* Wrgb = a.take<float>(3 * 256);
@@ -1439,7 +1467,7 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   for (int l = 0; l < 8; ++l) {
     int in = f.imp_in[l], out = f.imp_out[l];
     int nk = (l == 0) ? nk0 : 4;
-    pack_layer(c, s, f.imp_W[l], in, 0, 0, 0, out, (l == 0) ? E : in, nk, out * in);
+    pack_layer(c, P.step[s], f.imp_W[l], in, 0, 0, 0, out, (l == 0) ? E : in, nk, out * in);
     P.step[s].nk = nk;
     P.step[s].epi = EPI_SOFTPLUS;
     P.step[s].flags = F_SAVE_SIG | ((l == f.skip_layer - 1) ? F_INJECT_EMB : 0) | ((l == 7) ? F_SDF_DOT : 0);
@@ -1453,31 +1481,48 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   tb->sdf_prog.nsteps = 8;
   tb->sdf_prog.slots_per_tile = c.nslots;
   for (int i = 0; i < 8; ++i) tb->sdf_prog.step[i].flags &= ~F_SAVE_SIG;
-  // ---- L8 features ----
-  pack_layer(c, s, f.imp_W[8], 256, 0, 1, 0, 256, 256, 4, 257 * 256);
-  P.step[s].nk = 4;
-  P.step[s].epi = EPI_FEAT;
-  P.step[s].flags = F_FEAT_OUT;
-  P.step[s].sig = -1;
-  P.step[s].bias = b8feat;
-  P.step[s].ncols = 256;
-  ++s;
-  tb->fwd_prog = P;
-  tb->fwd_prog.nsteps = 9;
-  tb->fwd_prog.slots_per_tile = c.nslots;
-  for (int i = 0; i < 8; ++i) tb->fwd_prog.step[i].flags &= ~F_SAVE_SIG;
+  // ---- L8 features (operator API: sdf + features) ----
+  {
+    TcProgram F = P;
+    pack_layer(c, F.step[8], f.imp_W[8], 256, 0, 1, 0, 256, 256, 4, 257 * 256);
+    F.step[8].nk = 4;
+    F.step[8].epi = EPI_FEAT;
+    F.step[8].flags = F_FEAT_OUT;
+    F.step[8].sig = -1;
+    F.step[8].bias = b8feat;
+    F.step[8].ncols = 256;
+    F.nsteps = 9;
+    F.slots_per_tile = c.nslots;
+    for (int i = 0; i < 8; ++i) F.step[i].flags &= ~F_SAVE_SIG;
+    tb->fwd_prog = F;
+  }
   const bool fg_chain = (f.ren_mode == 0) && (f.n_ren == 5) && f.ren_out[0] == 256;
   const bool bg_chain = (f.ren_mode == 1) && (f.n_ren == 2) && f.ren_out[0] <= 256 && f.ren_extra <= 27;
   tb->has_full = fg_chain || bg_chain;
+  // The feature layer L8 and the colour layer 0 have no non-linearity in between (networks.py:199-207 -> :281,:305):
+  //   C0_pre = Wc0[:, feat] (W8[1:] h7 + b8[1:]) + Wc0[:, extra] extra + b0  =  M h7 + (Wc0f b8f + b0) + ...
+  // so the fused chains run ONE layer with M = Wc0[:, feat] . W8[1:, :] instead of two.
+  float* Mfold = a.take<float>(256 * 256);
+  f.ren_cb = a.take<float>(264);
+  f.ren_b0_fold = a.take<float>(264);
+  MP_REQUIRE(a.ok, "tc_pack: storage too small");
+  if (tb->has_full) {
+    const int in0 = f.ren_in[0] == 0 ? 0 : (f.ren_mode == 0 ? 6 + 8 + 256 : f.ren_extra + 32 + 256);
+    const int coff = f.ren_mode == 0 ? 14 : f.ren_extra + 32;
+    const int o0 = f.ren_out[0];
+    fold_mm_kernel<<<dim3(256 / 16, div_up(o0, 16)), dim3(16, 16), 0, st>>>(f.ren_W[0], in0, coff, f.imp_W[8] + 256, 256,
+                                                                          f.imp_b[8] + 1, o0, Mfold, f.ren_cb);
+    g_launches++;
+  }
   if (bg_chain) {
-    // background: colour layer 0 (view embedding + features -> 128, ReLU) and the rgb head (multiply.py:531)
-    const int in0 = f.ren_extra + 32 + 256, o0 = f.ren_out[0];
-    pack_layer(c, s, f.ren_W[0], in0, 0, 0, f.ren_extra + 32, o0, 256, 4, o0 * in0);
+    // background: folded colour layer 0 (view embedding + h7 -> 128, ReLU) and the rgb head (multiply.py:531)
+    const int o0 = f.ren_out[0];
+    pack_layer(c, P.step[s], Mfold, 256, 0, 0, 0, o0, 256, 4, 256 * 256);
     P.step[s].nk = 4;
     P.step[s].epi = EPI_RELU;
     P.step[s].flags = F_EXTRA_IN | F_RGB_OUT;
     P.step[s].sig = -1;
-    P.step[s].bias = f.ren_b0_eff;
+    P.step[s].bias = f.ren_b0_fold;
     P.step[s].ncols = o0;
     ++s;
     pad_rows_kernel<<<div_up(f.ren_extra * 256, 256), 256, 0, st>>>(f.ren_Wt[0], o0, f.ren_extra, o0, W0x);
@@ -1491,12 +1536,13 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
     for (int i = 0; i < 8; ++i) tb->full_prog.step[i].flags &= ~F_SAVE_SIG;   // no reverse sweep in the background
   }
   if (fg_chain) {
+    // h7 is parked (it returns as the folded colour layer's input) and the reverse sweep starts right after L7
     P.step[s - 1].flags |= F_SEED_BWD | F_STASH_FEAT;
     // ---- reverse sweep B7..B1: g_{l-1} = (g_l * sigma'_l) . W_l ----
     for (int l = 7; l >= 1; --l) {
       int in = f.imp_in[l], out = f.imp_out[l];
       // B[n][k] = W_l[k][n] : n over in (valid in), k over out (valid out)
-      pack_layer(c, s, f.imp_W[l], in, 1, 0, 0, in, out, 4, out * in);
+      pack_layer(c, P.step[s], f.imp_W[l], in, 1, 0, 0, in, out, 4, out * in);
       P.step[s].nk = 4;
       P.step[s].epi = EPI_BWD;
       P.step[s].flags = (l == f.skip_layer) ? F_SKIP_GRAD : 0;
@@ -1506,7 +1552,7 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
       ++s;
     }
     // ---- B0: d/d embed = (g_0 * sigma'_0) . W0[:, :E] ----
-    pack_layer(c, s, f.imp_W[0], f.imp_in[0], 1, 0, 0, E, 256, 4, 256 * f.imp_in[0]);
+    pack_layer(c, P.step[s], f.imp_W[0], f.imp_in[0], 1, 0, 0, E, 256, 4, 256 * f.imp_in[0]);
     P.step[s].nk = 4;
     P.step[s].epi = EPI_BWD;
     P.step[s].flags = F_FINAL_GRAD;
@@ -1514,15 +1560,17 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
     P.step[s].bias = nullptr;
     P.step[s].ncols = E;
     ++s;
-    // ---- colour net ----
+    // ---- colour net: folded layer 0, then layers 1..3 ----
     for (int l = 0; l < 4; ++l) {
-      int in = (l == 0) ? (6 + 8 + 256) : 256;
-      pack_layer(c, s, f.ren_W[l], in, 0, 0, (l == 0) ? 14 : 0, 256, 256, 4, 256 * in);
+      if (l == 0)
+        pack_layer(c, P.step[s], Mfold, 256, 0, 0, 0, 256, 256, 4, 256 * 256);
+      else
+        pack_layer(c, P.step[s], f.ren_W[l], 256, 0, 0, 0, 256, 256, 4, 256 * 256);
       P.step[s].nk = 4;
       P.step[s].epi = EPI_RELU;
       P.step[s].flags = ((l == 0) ? F_EXTRA_IN : 0) | ((l == 3) ? F_RGB_OUT : 0);
       P.step[s].sig = -1;
-      P.step[s].bias = (l == 0) ? f.ren_b0_eff : f.ren_b[l];
+      P.step[s].bias = (l == 0) ? f.ren_b0_fold : f.ren_b[l];
       P.step[s].ncols = 256;
       ++s;
     }
