@@ -85,6 +85,7 @@ struct GridHeader {
   float h;
   int dim[3];
   int ncell;
+  int R0;        // search radius in cells that covers the query radius the grid was built for (h * R0 >= radius)
 };
 constexpr int kMaxCells = 32768;
 
@@ -103,6 +104,7 @@ struct Body {
   int* posed_cell_start;
   float4* posed_sorted;
   int* scratch;              // [kMaxCells + 8]
+  float4* vert_tf;           // [V][3] per-vertex inverse blended transform: rows (I_r0, I_r1, I_r2, c_r), x_c = I (x - c)
 };
 
 // packed network (mlp_pack.cu)

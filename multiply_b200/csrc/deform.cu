@@ -15,7 +15,7 @@ namespace mp {
 // -------------------------------------------------------------------------------------------
 // grid build: single CTA (V = 6890 is tiny); bbox -> cell size -> histogram -> scan -> scatter
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restrict__ verts, int V, float cell,
+__global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restrict__ verts, int V, float cell, int R0,
                                                           GridHeader* __restrict__ hdr,
                                                           int* __restrict__ cell_start, float4* __restrict__ sorted,
                                                           int* __restrict__ cursor) {
@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restric
       ext = fmaxf(ext, h - l);
     }
     float h = cell;
-    // Two empty border cells on every side: a query within 2h of the vertex bounding box still has its own
-    // cell inside the grid, which is what the optimality proof of nearest_vertex() needs.  Keep the grid
-    // within kMaxCells.
+    // 2*R0 empty border cells on every side: a query within 2*R0*h of the vertex bounding box still has its
+    // own cell inside the grid, which is what the optimality proof of nearest_vertex() needs.  Keep the grid
+    // within kMaxCells (growing h only makes R0 cells cover more than the radius).
+    const int pad = 2 * R0;
     for (;;) {
       long long n = 1;
       for (int a = 0; a < 3; ++a) {
-        g.dim[a] = (int)floorf((s_hi[a][0] - g.lo[a]) / h) + 1 + 4;
+        g.dim[a] = (int)floorf((s_hi[a][0] - g.lo[a]) / h) + 1 + 2 * pad;
         n *= g.dim[a];
       }
       if (n <= kMaxCells) {
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(const float* __restric
       }
       h *= 1.25f;
     }
-    for (int a = 0; a < 3; ++a) g.lo[a] -= 2.f * h;
+    for (int a = 0; a < 3; ++a) g.lo[a] -= (float)pad * h;
+    g.R0 = R0;
     g.h = h;
     g.inv_h = 1.0f / h;
     *hdr = g;
@@ -190,19 +192,23 @@ __device__ __forceinline__ void nearest_vertex(const GridHeader& g, const int* _
   bool inside = cx >= 0 && cy >= 0 && cz >= 0 && cx < g.dim[0] && cy < g.dim[1] && cz < g.dim[2];
   float hh = g.h * 0.999f;
   if (!full_scan_if_unsure) {
-    // outlier classification only: any vertex within the 0.1 radius lies in the 3x3x3 block (cell >= 0.1001).
-    // The grid carries two empty border cells, so a query whose cell is not in [1, dim-2] on some axis has
+    // outlier classification only: any vertex within the 0.1 radius lies in the (2 R0 + 1)^3 block (R0 h >= 0.1001).
+    // The grid carries 2 R0 empty border cells, so a query whose cell is not in [R0, dim-1-R0] on some axis has
     // no vertex in its block at all: the common case for samples far from the body.
-    if (cx < 1 || cy < 1 || cz < 1 || cx > g.dim[0] - 2 || cy > g.dim[1] - 2 || cz > g.dim[2] - 2) return;
-    scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
+    const int R0 = g.R0;
+    if (cx < R0 || cy < R0 || cz < R0 || cx > g.dim[0] - 1 - R0 || cy > g.dim[1] - 1 - R0 || cz > g.dim[2] - 1 - R0)
+      return;
+    scan_block(g, cell_start, sorted, cx, cy, cz, R0, px, py, pz, best, bi);
     return;
   }
-  scan_block(g, cell_start, sorted, cx, cy, cz, 1, px, py, pz, best, bi);
-  bool proven = inside && best <= hh * hh;
+  const int R0 = g.R0;
+  scan_block(g, cell_start, sorted, cx, cy, cz, R0, px, py, pz, best, bi);
+  float rr = (float)R0 * hh;
+  bool proven = inside && best <= rr * rr;
   if (!proven && inside) {
-    // the 3x3x3 block proved nothing: widen to 5x5x5 (the scan keeps `best`, so already-pruned cells stay pruned)
-    scan_block(g, cell_start, sorted, cx, cy, cz, 2, px, py, pz, best, bi);
-    proven = best <= 4.f * hh * hh;
+    // the first block proved nothing: double the radius (the scan keeps `best`, so pruned cells stay pruned)
+    scan_block(g, cell_start, sorted, cx, cy, cz, 2 * R0, px, py, pz, best, bi);
+    proven = best <= 4.f * rr * rr;
   }
   if (!proven) {
     best = INFINITY;
@@ -252,6 +258,23 @@ __device__ __forceinline__ void inv3(const float* A, int ld, float* I) {
   I[8] = (a * e - b * d) * r;
 }
 
+// Per-frame table: the blended transform only depends on the VERTEX whose weights are used (K = 1, weights
+// detached, deformer.py:37-50), so T_v = sum_j W[v][j] tfs_j and its closed-form inverse are computed once per
+// vertex (6890) instead of once per sample point (millions): x_c = I_v (x - t_v / s_v), J^-1 = I_v.
+__global__ void vertex_tf_kernel(const float* __restrict__ weights, const float* __restrict__ tfs, int V,
+                                 float4* __restrict__ vert_tf) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float T[12], s;
+  blend_tf(weights + (size_t)v * MP_NUM_JOINTS, tfs, T, s);
+  float I[9];
+  inv3(T, 4, I);
+  float is = 1.0f / s;
+  vert_tf[3 * (size_t)v + 0] = make_float4(I[0], I[1], I[2], T[3] * is);
+  vert_tf[3 * (size_t)v + 1] = make_float4(I[3], I[4], I[5], T[7] * is);
+  vert_tf[3 * (size_t)v + 2] = make_float4(I[6], I[7], I[8], T[11] * is);
+}
+
 // Shared per-point routine of the inverse deformer.
 __device__ __forceinline__ void deform_inverse_point(const Body& b, const GridHeader& g, float px, float py, float pz,
                                                      bool exact_far, float xc[3], bool& outlier) {
@@ -268,16 +291,13 @@ __device__ __forceinline__ void deform_inverse_point(const Body& b, const GridHe
     xc[2] = pz;
     return;
   }
-  float T[12], s;
-  blend_tf(b.weights + (size_t)vi * MP_NUM_JOINTS, b.tfs, T, s);
-  float I[9];
-  inv3(T, 4, I);
-  // [A t; 0 s]^-1 [x;1] = A^-1 (x - t/s)
-  float is = 1.0f / s;
-  float qx = px - T[3] * is, qy = py - T[7] * is, qz = pz - T[11] * is;
-  xc[0] = I[0] * qx + I[1] * qy + I[2] * qz;
-  xc[1] = I[3] * qx + I[4] * qy + I[5] * qz;
-  xc[2] = I[6] * qx + I[7] * qy + I[8] * qz;
+  // [A t; 0 s]^-1 [x;1] = A^-1 (x - t/s), from the per-vertex table
+  const float4 r0 = __ldg(&b.vert_tf[3 * (size_t)vi]), r1 = __ldg(&b.vert_tf[3 * (size_t)vi + 1]),
+               r2 = __ldg(&b.vert_tf[3 * (size_t)vi + 2]);
+  float qx = px - r0.w, qy = py - r1.w, qz = pz - r2.w;
+  xc[0] = r0.x * qx + r0.y * qy + r0.z * qz;
+  xc[1] = r1.x * qx + r1.y * qy + r1.z * qz;
+  xc[2] = r2.x * qx + r2.y * qy + r2.z * qz;
 }
 
 __global__ void deform_inverse_kernel(Body b, const float* __restrict__ x, int N, float* __restrict__ x_c,
@@ -356,31 +376,31 @@ __global__ void deform_forward_jac_kernel(Body b, const float* __restrict__ x_c,
   float d2;
   int vi;
   nearest_vertex(g, b.cano_cell_start, b.cano_sorted, b.V, px, py, pz, true, d2, vi);
-  float T[12], s;
-  blend_tf(b.weights + (size_t)vi * MP_NUM_JOINTS, b.tfs, T, s);
   if (x_d) {
+    float T[12], s;
+    blend_tf(b.weights + (size_t)vi * MP_NUM_JOINTS, b.tfs, T, s);
     x_d[3 * i] = T[0] * px + T[1] * py + T[2] * pz + T[3];
     x_d[3 * i + 1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
     x_d[3 * i + 2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
   }
   if (Jinv) {
-    float I[9];
-    inv3(T, 4, I);
+    const float4 r0 = __ldg(&b.vert_tf[3 * (size_t)vi]), r1 = __ldg(&b.vert_tf[3 * (size_t)vi + 1]),
+                 r2 = __ldg(&b.vert_tf[3 * (size_t)vi + 2]);
     if (jstride == 12) {   // padded rows: three 128-bit stores
       float4* o = reinterpret_cast<float4*>(Jinv + 12 * (size_t)i);
-      o[0] = make_float4(I[0], I[1], I[2], I[3]);
-      o[1] = make_float4(I[4], I[5], I[6], I[7]);
-      o[2] = make_float4(I[8], 0.f, 0.f, 0.f);
+      o[0] = make_float4(r0.x, r0.y, r0.z, r1.x);
+      o[1] = make_float4(r1.y, r1.z, r2.x, r2.y);
+      o[2] = make_float4(r2.z, 0.f, 0.f, 0.f);
     } else {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Jinv[9 * (size_t)i + k] = I[k];
+      float* o = Jinv + 9 * (size_t)i;
+      o[0] = r0.x; o[1] = r0.y; o[2] = r0.z; o[3] = r1.x; o[4] = r1.y; o[5] = r1.z; o[6] = r2.x; o[7] = r2.y; o[8] = r2.z;
     }
   }
 }
 
-int body_build_grid(const float* verts, int V, float cell, GridHeader* hdr, int* cell_start, float4* sorted,
+int body_build_grid(const float* verts, int V, float cell, int R0, GridHeader* hdr, int* cell_start, float4* sorted,
                     int* scratch, cudaStream_t st) {
-  grid_build_kernel<<<1, 1024, 0, st>>>(verts, V, cell, hdr, cell_start, sorted, scratch);
+  grid_build_kernel<<<1, 1024, 0, st>>>(verts, V, cell, R0, hdr, cell_start, sorted, scratch);
   MP_LAUNCH_CHECK();
   return 0;
 }
@@ -416,6 +436,7 @@ size_t mp_body_bytes(int V) {
   n += mp::align_up((mp::kMaxCells + 1) * sizeof(int), 256) * 2;
   n += mp::align_up((size_t)V * sizeof(float4), 256) * 2;
   n += mp::align_up((mp::kMaxCells + 8) * sizeof(int), 256);
+  n += mp::align_up((size_t)V * 3 * sizeof(float4), 256);
   return n + 1024;
 }
 
@@ -441,12 +462,13 @@ int mp_body_create(const float* verts_cano, const float* weights, int V, float c
   b.cano_sorted = a.take<float4>(V);
   b.posed_sorted = a.take<float4>(V);
   b.scratch = a.take<int>(mp::kMaxCells + 8);
+  b.vert_tf = a.take<float4>((size_t)V * 3);
   if (!a.ok) {
     delete h;
     mp::set_error("mp_body_create: arena overflow");
     return -1;
   }
-  int r = mp::body_build_grid(verts_cano, V, cano_cell, b.cano_hdr, b.cano_cell_start, b.cano_sorted, b.scratch,
+  int r = mp::body_build_grid(verts_cano, V, cano_cell * 0.5f, 2, b.cano_hdr, b.cano_cell_start, b.cano_sorted, b.scratch,
                               (cudaStream_t)stream);
   if (r) {
     delete h;
@@ -463,8 +485,11 @@ int mp_body_set_pose(mp_body_t* h, const float* verts_posed, const float* tfs, v
   mp::Body& b = h->b;
   b.verts_posed = verts_posed;
   b.tfs = tfs;
-  // cell = 0.1001 > the 0.1 outlier radius of deformer.py:49 (see nearest_vertex)
-  return mp::body_build_grid(verts_posed, b.V, 0.1001f, b.posed_hdr, b.posed_cell_start, b.posed_sorted, b.scratch,
+  mp::vertex_tf_kernel<<<mp::div_up(b.V, 128), 128, 0, (cudaStream_t)stream>>>(b.weights, tfs, b.V, b.vert_tf);
+  MP_LAUNCH_CHECK();
+  // two cells of 0.05005 cover the 0.1 outlier radius of deformer.py:49 (see nearest_vertex); the finer cells let
+  // the distance pruning of scan_block skip most of the block
+  return mp::body_build_grid(verts_posed, b.V, 0.05005f, 2, b.posed_hdr, b.posed_cell_start, b.posed_sorted, b.scratch,
                              (cudaStream_t)stream);
 }
 
