@@ -304,9 +304,21 @@ __device__ __forceinline__ void tmem_wait<32>(float* v) {
 }
 
 // NW epilogue warps (8 or 16): warp w owns TMEM lane quadrant w % 4 (rows) and column part (w-2)/4.
-template <int NW>
+//
+// PIPE (NW = 16 only): K-block-granular hand-over between the epilogue and the MMA issuer.
+//   * a column part no longer owns one 64-column K-block of the next layer's operand; it owns 16 columns of
+//     each of the four, visited in K-block order, and arrives on a per-K-block barrier after each chunk.  The
+//     next layer's MMAs over K-block kb therefore start after a quarter of the epilogue instead of after all
+//     of it;
+//   * those MMAs write a second accumulator (TMEM columns 256..511, alternating per step) because the
+//     epilogue is still draining the first.
+//   The operand A stays single-buffered: all MMAs of a step have completed before its epilogue starts.
+template <int NW, bool PIPE>
 __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
                                                                    const __grid_constant__ TcIO io) {
+  static_assert(!PIPE || NW == 16, "PIPE needs four column parts of 16-column chunks");
+  constexpr int NBAR = PIPE ? 4 : 1;       // operand hand-over barriers (one per K-block when pipelined)
+  constexpr int TCOLS = PIPE ? 512 : 256;  // TMEM columns
   constexpr int NPART = NW / 4;            // column parts
   constexpr int PCOLS = 256 / NPART;       // columns per part
   constexpr int CW = (NW == 16) ? 16 : 32; // columns per TMEM load (register budget)
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   uint64_t* empty = bars + kRing;                   // [kRing]
   uint64_t* d_full = bars + 2 * kRing;
   uint64_t* a_ready = bars + 2 * kRing + 1;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kRing + 2);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kRing + 1 + NBAR);
 
   const int count = io.count ? min(io.cap, *io.count) : io.cap;
   const int ntiles = (count + 127) >> 7;
@@ -334,18 +346,19 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       mbar_init(&empty[i], 1);
     }
     mbar_init(d_full, 1);
-    mbar_init(a_ready, NEPI);
+    for (int i = 0; i < NBAR; ++i) mbar_init(&a_ready[i], NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot))
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem0 = *tmem_slot;
 
   if (warp == 0) {
     // ===================== weight loader =====================
@@ -370,15 +383,21 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
       const uint32_t a_hi = smem_u32(A), a_lo = smem_u32(A) + 65536;
-      uint32_t it = 0, ar_ph = 0;
+      uint32_t it = 0, ar_ph = 0, buf = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int s = 0; s < P.nsteps; ++s) {
-          mbar_wait(a_ready, ar_ph);
-          ar_ph ^= 1;
-          tc_fence_after();
+          if (!PIPE) {
+            mbar_wait(a_ready, ar_ph);
+            tc_fence_after();
+          }
           const int nk = P.step[s].nk;
+          const uint32_t tmem = tmem0 + (PIPE ? buf * 256u : 0u);
           uint32_t acc = 0;
           for (int kc = 0; kc < nk; ++kc) {
+            if (PIPE) {
+              mbar_wait(&a_ready[kc], ar_ph);
+              tc_fence_after();
+            }
             // hi slot: A_hi.W_hi + A_lo.W_hi
             int r = it % kRing;
             mbar_wait(&full[r], (it / kRing) & 1);
@@ -405,6 +424,12 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             ++it;
           }
           umma_commit(d_full);
+          if (PIPE) {
+            // keep the phases of the unused K-block barriers in step
+            for (int kc = nk; kc < 4; ++kc) mbar_wait(&a_ready[kc], ar_ph);
+            buf ^= 1;
+          }
+          ar_ph ^= 1;
         }
       }
     }
@@ -413,7 +438,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int part = (warp - 2) >> 2;       // column part
     const int row = q * 32 + lane;
-    const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_row0 = tmem0 + ((uint32_t)(q * 32) << 16);
+    uint32_t ebuf = 0;                       // accumulator the next step drains (PIPE)
     char* scr = io.scratch + (size_t)blockIdx.x * io.scratch_per_cta;
     float4* sig = (float4*)scr;                                  // [8][64][128]
     uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
@@ -422,6 +448,15 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     uint32_t df_ph = 0;
     const int d = P.d_in, E = P.E;
     const int cbeg = part * PCOLS, cend = cbeg + PCOLS;
+    constexpr int NCH = PCOLS / CW;          // chunks per thread and step
+    // first column of this thread's i-th chunk: contiguous, or 16 columns of every K-block in K order (PIPE)
+    auto col_of = [&](int i) { return PIPE ? i * 64 + part * CW : cbeg + i * CW; };
+    auto arrive_all = [&]() {
+      fence_async_smem();
+      tc_fence_before();
+#pragma unroll
+      for (int i = 0; i < NBAR; ++i) mbar_arrive(&a_ready[i]);
+    };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int pt = tile * 128 + row;
       const bool valid = pt < count;
@@ -454,8 +489,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? ge[(size_t)(c + j) * 128 + row] : 0.f;
           store_a8(A, row, c, v);
         }
-        fence_async_smem();
-        mbar_arrive(a_ready);
+        arrive_all();
       }
       // colour-net extra inputs: foreground [x_c, n] (networks.py:281), background view-dir embedding (:275)
       float xin[27];
@@ -479,15 +513,20 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
         if (need_sig) {
 #pragma unroll
-          for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((cbeg >> 2) + g4)) * 128 + row];
+          for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((col_of(0) >> 2) + g4)) * 128 + row];
         }
         mbar_wait(d_full, df_ph);
         df_ph ^= 1;
         tc_fence_after();
+        const uint32_t t_row = t_row0 + (PIPE ? ebuf * 256u : 0u);
+        ebuf ^= 1;
+        // steps whose operand for the next step is complete chunk by chunk (no tail rewrites A)
+        const bool chunk_handover = PIPE && s + 1 < P.nsteps && !(st.flags & (F_RGB_OUT | F_FINAL_GRAD | F_SEED_BWD));
         if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
         float va[CW];
-        auto process_chunk = [&](float* v, float* vnext, const int c) {
+        auto process_chunk = [&](float* v, const int ci) {
+          const int c = col_of(ci);
           tmem_wait<CW>(v);
           if (st.epi == EPI_SOFTPLUS) {
             float4 b4[G4];
@@ -571,10 +610,10 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 v[4 * g4 + 3] *= isc * s4[g4].w;
               }
             }
-            if (need_sig && c + CW < cend) {   // next chunk's sigma' streams in behind the stores below
+            if (need_sig && ci + 1 < NCH) {   // next chunk's sigma' streams in behind the stores below
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4)
-                s4[g4] = sig[((size_t)st.sig * 64 + (((c + CW) >> 2) + g4)) * 128 + row];
+                s4[g4] = sig[((size_t)st.sig * 64 + ((col_of(ci + 1) >> 2) + g4)) * 128 + row];
             }
           } else {   // EPI_RELU
 #pragma unroll
@@ -631,9 +670,16 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           }
         };
         // (double-buffering the TMEM reads was measured slower: +20 % kernel time from spills / code size)
-        for (int c = cbeg; c < cend; c += CW) {
-          tmem_issue<CW>(t_row + (uint32_t)c, va);
-          process_chunk(va, va, c);
+#pragma unroll 1
+        for (int ci = 0; ci < NCH; ++ci) {
+          tmem_issue<CW>(t_row + (uint32_t)col_of(ci), va);
+          process_chunk(va, ci);
+          if (chunk_handover) {
+            // K-block ci of the next layer's operand is complete in this thread
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&a_ready[ci]);
+          }
         }
         tc_fence_before();
         // ---- step-specific tails ----
@@ -740,17 +786,14 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         }
         // hand A (and the drained accumulator) to the MMA warp for the next step of this tile;
         // the last step's hand-over is the next tile's prologue arrival
-        if (s + 1 < P.nsteps) {
-          fence_async_smem();
-          mbar_arrive(a_ready);
-        }
+        if (s + 1 < P.nsteps && !chunk_handover) arrive_all();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(TCOLS) : "memory");
   }
 }
 
@@ -1667,6 +1710,7 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
   }
   static bool attr_set = false;
   static int nw = 16;
+  static int pipe = 1; // K-block-granular hand-over with two accumulators (MP_TC_PIPE=0: whole-layer hand-over)
   static int v2 = 0;   // overlapped TS-mode variant: correct (all parity tests) but measured 6 % slower, see profiles/
   if (!attr_set) {
     const char* e = getenv("MP_TC_EPI_WARPS");
@@ -1674,9 +1718,12 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
     const char* e2 = getenv("MP_TC_V2");
     if (e2) v2 = atoi(e2);
     if (nw != 16) v2 = 0;
+    const char* e3 = getenv("MP_TC_PIPE");
+    if (e3) pipe = atoi(e3);
     MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel_v2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   ProfEntry pe;
@@ -1695,10 +1742,12 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
   }
   if (v2)
     tc_chain_kernel_v2<16><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
+  else if (nw == 16 && pipe)
+    tc_chain_kernel<16, true><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
   else if (nw == 16)
-    tc_chain_kernel<16><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
+    tc_chain_kernel<16, false><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
   else
-    tc_chain_kernel<8><<<grid, 64 + 32 * 8, kSmemBytes, st>>>(P, io);
+    tc_chain_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, st>>>(P, io);
   MP_LAUNCH_CHECK();
   if (prof) {
     MP_CHECK_CUDA(cudaEventRecord(pe.e1, st));
