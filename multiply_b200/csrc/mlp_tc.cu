@@ -80,7 +80,6 @@ struct TcIO {
   float* nrm_out;        // [slots,3]
   float* grad_out;       // [cap,3] dense or nullptr
   float* feat_out;       // [cap,256] dense or nullptr
-  int variant;           // timing experiments on the v2 kernel (MP_TC_VARIANT): 1 = operand always in smem, 2 = no half hand-over
   char* scratch;         // per-CTA scratch
   size_t scratch_per_cta;
 };
@@ -90,7 +89,8 @@ constexpr size_t kSigBytes = (size_t)8 * 64 * 128 * 16;      // sigma' [8][64][1
 constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo chunks
 constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
 constexpr size_t kMiscBytes = (size_t)128 * 32 * 4;          // partial sums / normals [128][32]
-constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes;
+constexpr size_t kEmbBytes = (size_t)96 * 128 * 4;           // input embedding of the tile [E<=96][128]
+constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes;
 
 // shared memory carve-up
 constexpr int kABytes = 2 * 4 * 128 * 128;                   // hi + lo, 4 K-blocks of [128 x 128B]
@@ -214,7 +214,7 @@ __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(
 // softplus(beta=100, threshold=20) and its derivative (networks.py:85)
 // Branch-free so that the elements of a chunk pipeline through the MUFU unit (a per-element branch serialises
 // them: measured 5x slower).  Raw MUFU approximations (ex2 / lg2 / rcp .approx.ftz) without the
-// denormal fix-ups of __expf/__logf: arguments are clamped to [-inf, 20*log2(e)] and 1+u >= 1, results only need
+// denormal fix-ups of __expf/__logf: 1+u >= 1, the overflow side is replaced by the linear branch, results only need
 // ~1e-7 absolute accuracy (softplus = log1p(exp(100 z))/100).
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -233,13 +233,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float softplus_fast(float z) {
   float t = z * 144.26950408889634f;                 // 100 z log2(e)
-  float u = ex2_approx(fminf(t, 28.853900817779268f));
+  float u = ex2_approx(t);                           // inf above ~128: discarded by the select below
   float y = lg2_approx(1.f + u) * 0.0069314718055994531f;   // ln2 / 100
   return t > 28.853900817779268f ? z : y;
 }
 __device__ __forceinline__ void softplus_fast_grad(float z, float& y, float& d) {
   float t = z * 144.26950408889634f;
-  float u = ex2_approx(fminf(t, 28.853900817779268f));
+  float u = ex2_approx(t);                           // inf above ~128: u * rcp(inf) = NaN, discarded below
   float w = 1.f + u;
   float r = rcp_approx(w);
   float ys = lg2_approx(w) * 0.0069314718055994531f;
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
     float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
     float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
+    float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes);   // [96][128]
     uint32_t df_ph = 0;
     const int d = P.d_in, E = P.E;
     const int cbeg = part * PCOLS, cend = cbeg + PCOLS;
@@ -467,18 +468,18 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
       {
         // positional embedding (embedders.py:8-34): the (frequency, axis) pairs of a row are split over its
-        // column-part threads, one sincosf each, parked in scratch (the `ge` region is free until the reverse
-        // sweep) so that the skip connection of layer 4 re-reads instead of recomputing them
+        // column-part threads, one sincosf each, parked in scratch so that the skip connection of layer 4 and
+        // the chain rule at the end of the reverse sweep re-read instead of recomputing them
         const int npair = d * P.multires;
         for (int pi = part; pi < npair; pi += NPART) {
           int f = pi / d, a = pi - f * d;
           float sn, cs;
           sincosf(__fmul_rn(x[a], (float)(1 << f)), &sn, &cs);
-          ge[(size_t)(d + 2 * f * d + a) * 128 + row] = sn;
-          ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row] = cs;
+          emb[(size_t)(d + 2 * f * d + a) * 128 + row] = sn;
+          emb[(size_t)(d + (2 * f + 1) * d + a) * 128 + row] = cs;
         }
         if (part == 0)
-          for (int a = 0; a < d; ++a) ge[(size_t)a * 128 + row] = x[a];
+          for (int a = 0; a < d; ++a) emb[(size_t)a * 128 + row] = x[a];
         __threadfence_block();
         ep_bar<NEPI>();
         const int ncol = P.step[0].nk * 64;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         for (int c = c0; c < c1; c += 8) {
           float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? ge[(size_t)(c + j) * 128 + row] : 0.f;
+          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? emb[(size_t)(c + j) * 128 + row] : 0.f;
           store_a8(A, row, c, v);
         }
         arrive_all();
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             if ((st.flags & F_INJECT_EMB) && c + CW > P.inj_col) {
 #pragma unroll
               for (int j = 0; j < CW; ++j)
-                if (c + j >= P.inj_col) v[j] = ge[(size_t)(c + j - P.inj_col) * 128 + row];
+                if (c + j >= P.inj_col) v[j] = emb[(size_t)(c + j - P.inj_col) * 128 + row];
             }
             if (st.flags & F_SDF_DOT) {
 #pragma unroll
@@ -625,16 +626,21 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
             }
             if (st.flags & F_EXTRA_IN) {
-              for (int e = 0; e < P.n_extra; ++e) {
-                const float xe = xin[e];
-                const float4* w4 = (const float4*)(P.W0x + e * 256 + c);
+              // n_extra is 6 (foreground) or 27 (background): three inputs per trip keep 12 weight loads in flight
+              for (int e0 = 0; e0 < P.n_extra; e0 += 3) {
 #pragma unroll
-                for (int j4 = 0; j4 < G4; ++j4) {
-                  float4 ww = __ldg(w4 + j4);
-                  v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
-                  v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
-                  v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
-                  v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
+                for (int u = 0; u < 3; ++u) {
+                  const int e = e0 + u;
+                  const float xe = e < P.n_extra ? xin[e] : 0.f;
+                  const float4* w4 = (const float4*)(P.W0x + (e < P.n_extra ? e : 0) * 256 + c);
+#pragma unroll
+                  for (int j4 = 0; j4 < G4; ++j4) {
+                    float4 ww = __ldg(w4 + j4);
+                    v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
+                    v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
+                    v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
+                    v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
+                  }
                 }
               }
             }
@@ -711,61 +717,83 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         if (st.flags & F_FINAL_GRAD) {
           __threadfence_block();
           ep_bar<NEPI>();
-          if (part == 0) {
-            // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos)
-            float g[3] = {0.f, 0.f, 0.f};
-            for (int a = 0; a < d && a < 3; ++a) {
-              float acc = ge[(size_t)a * 128 + row];
-              for (int f = 0; f < P.multires; ++f) {
-                float fr = (float)(1 << f);
-                float t = __fmul_rn(x[a], fr);
-                float sn, cs;
-                sincosf(t, &sn, &cs);
-                float gs = ge[(size_t)(d + 2 * f * d + a) * 128 + row];
-                float gc = ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row];
-                acc += fr * (cs * gs - sn * gc);
+          // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos).  The (frequency, axis) pairs
+          // of a row are split over its column-part threads; sin / cos come back from the prologue's scratch.
+          {
+            float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+            const int npair = d * P.multires;
+            for (int pi = part; pi < npair; pi += NPART) {
+              const int f = pi / d, a = pi - f * d;
+              const size_t is = (size_t)(d + 2 * f * d + a) * 128 + row, ic = (size_t)(d + (2 * f + 1) * d + a) * 128 + row;
+              const float term = (float)(1 << f) * (emb[ic] * ge[is] - emb[is] * ge[ic]);
+              gp0 += a == 0 ? term : 0.f;
+              gp1 += a == 1 ? term : 0.f;
+              gp2 += a == 2 ? term : 0.f;
+            }
+            if (part == 0) {
+              gp0 += ge[row];
+              if (d > 1) gp1 += ge[128 + row];
+              if (d > 2) gp2 += ge[256 + row];
+            }
+            misc[row * 32 + 20 + part * 3 + 0] = gp0;
+            misc[row * 32 + 20 + part * 3 + 1] = gp1;
+            misc[row * 32 + 20 + part * 3 + 2] = gp2;
+          }
+          // features back into A for the colour net (independent of the gradient: fills the barrier wait)
+          if (s + 1 < P.nsteps) {
+#pragma unroll
+            for (int c8 = 0; c8 < PCOLS / 8; c8 += 4) {
+              uint4 fh[4], fl[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int chunk = (cbeg >> 3) + c8 + u;
+                fh[u] = fsc[(size_t)chunk * 128 + row];
+                fl[u] = fsc[(size_t)(32 + chunk) * 128 + row];
               }
-              g[a] = acc;
-            }
-            if (io.grad_out && valid) {
-              io.grad_out[3 * (size_t)pt] = g[0];
-              io.grad_out[3 * (size_t)pt + 1] = g[1];
-              io.grad_out[3 * (size_t)pt + 2] = g[2];
-            }
-            float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-            if (io.jinv && valid) {
-              const float* J = io.jinv + 12 * (size_t)pt;
-              float v0 = g[0] * J[0] + g[1] * J[3] + g[2] * J[6];
-              float v1 = g[0] * J[1] + g[1] * J[4] + g[2] * J[7];
-              float v2 = g[0] * J[2] + g[1] * J[5] + g[2] * J[8];
-              float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
-              v0 /= nr; v1 /= nr; v2 /= nr;
-              float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
-              n0 = v0 / n2r; n1 = v1 / n2r; n2 = v2 / n2r;
-              if (io.nrm_out) {
-                io.nrm_out[3 * (size_t)slot] = n0;
-                io.nrm_out[3 * (size_t)slot + 1] = n1;
-                io.nrm_out[3 * (size_t)slot + 2] = n2;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int chunk = (cbeg >> 3) + c8 + u;
+                const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
+                *reinterpret_cast<uint4*>(A + o) = fh[u];
+                *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
               }
             }
-            misc[row * 32 + 4] = n0;
-            misc[row * 32 + 5] = n1;
-            misc[row * 32 + 6] = n2;
           }
           __threadfence_block();
           ep_bar<NEPI>();
-          xin[3] = misc[row * 32 + 4];
-          xin[4] = misc[row * 32 + 5];
-          xin[5] = misc[row * 32 + 6];
-          // features back into A for the colour net
-          if (s + 1 < P.nsteps) {
-            for (int c = cbeg; c < cend; c += 8) {
-              int chunk = c >> 3;
-              uint32_t o = a_off(row, c >> 6, chunk & 7);
-              *reinterpret_cast<uint4*>(A + o) = fsc[(size_t)chunk * 128 + row];
-              *reinterpret_cast<uint4*>(A + 65536 + o) = fsc[(size_t)(32 + chunk) * 128 + row];
+          float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int pp = 0; pp < NPART; ++pp) {
+            g[0] += misc[row * 32 + 20 + pp * 3 + 0];
+            g[1] += misc[row * 32 + 20 + pp * 3 + 1];
+            g[2] += misc[row * 32 + 20 + pp * 3 + 2];
+          }
+          if (part == 0 && io.grad_out && valid) {
+            io.grad_out[3 * (size_t)pt] = g[0];
+            io.grad_out[3 * (size_t)pt + 1] = g[1];
+            io.grad_out[3 * (size_t)pt + 2] = g[2];
+          }
+          // every column part needs the normal as a colour input: all of them derive it (no second broadcast)
+          float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+          if (io.jinv && valid) {
+            const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
+            const float4 ja = J4[0], jb = J4[1], jc = J4[2];      // J[0..3], J[4..7], J[8..11]
+            float v0 = g[0] * ja.x + g[1] * ja.w + g[2] * jb.z;
+            float v1 = g[0] * ja.y + g[1] * jb.x + g[2] * jb.w;
+            float v2 = g[0] * ja.z + g[1] * jb.y + g[2] * jc.x;
+            float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
+            v0 /= nr; v1 /= nr; v2 /= nr;
+            float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
+            n0 = v0 / n2r; n1 = v1 / n2r; n2 = v2 / n2r;
+            if (part == 0 && io.nrm_out) {
+              io.nrm_out[3 * (size_t)slot] = n0;
+              io.nrm_out[3 * (size_t)slot + 1] = n1;
+              io.nrm_out[3 * (size_t)slot + 2] = n2;
             }
           }
+          xin[3] = n0;
+          xin[4] = n1;
+          xin[5] = n2;
         }
         if (st.flags & F_RGB_OUT) {
           misc[row * 32 + 8 + part * 3 + 0] = dot0;
@@ -794,551 +822,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(TCOLS) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// v2: MMA / epilogue overlap inside a tile.
-//   * the accumulator is split in two N-halves D0 | D1 (128 TMEM columns each, UMMA N = 128);
-//   * the activations ping-pong between shared memory (SS-mode MMA) and tensor memory (TS-mode MMA: the A operand
-//     is read from TMEM columns 256..511, fp16 pairs per 32-bit column, hi then lo), so the epilogue of half 0
-//     can write the next layer's operand while the MMAs of half 1 are still reading the current one;
-//   * layer l+1 starts on K-chunks 0,1 as soon as half 0 of layer l has been written back.
-// Weight slots are the two 128-row halves of the v1 slots (a [128 x 64] SW128 tile is the first / second
-// 16 KB of a [256 x 64] one), streamed through a 6-deep ring.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& w) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(w.x), "r"(w.y),
-               "r"(w.z), "r"(w.w)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-constexpr int kHalfSlot = 16384;
-constexpr int kRing2 = 6;
-constexpr uint32_t kTHi = 256, kTLo = 384;   // TMEM columns of the activation operand (hi | lo)
-
-// 8 consecutive output columns of one row -> next layer's A operand (shared memory or tensor memory)
-__device__ __forceinline__ void store_out8(bool to_tmem, char* A, uint32_t t_row, int row, int col, const float* v) {
-  uint4 hi, lo;
-  split8(v, hi, lo);
-  if (to_tmem) {
-    tmem_st4(t_row + kTHi + (uint32_t)(col >> 1), hi);
-    tmem_st4(t_row + kTLo + (uint32_t)(col >> 1), lo);
-  } else {
-    uint32_t o = a_off(row, col >> 6, (col >> 3) & 7);
-    *reinterpret_cast<uint4*>(A + o) = hi;
-    *reinterpret_cast<uint4*>(A + 65536 + o) = lo;
-  }
-}
-
-template <int NW>
-__global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel_v2(const __grid_constant__ TcProgram P,
-                                                                   const __grid_constant__ TcIO io) {
-  constexpr int NPART = NW / 4;            // column parts (per N-half)
-  constexpr int PCOLS = 128 / NPART;       // columns per part and half
-  constexpr int CW = 16;                   // columns per TMEM load
-  constexpr int G4 = CW / 4;
-  constexpr int NEPI = 32 * NW;
-  extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
-  char* base = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  char* A = base;                                   // [hi | lo] x 4 K-blocks
-  char* ring = base + kABytes;                      // kRing2 half-slots
-  uint64_t* bars = (uint64_t*)(ring + kRing2 * kHalfSlot);
-  uint64_t* full = bars;                            // [kRing2]
-  uint64_t* empty = bars + kRing2;                  // [kRing2]
-  uint64_t* d_full = bars + 2 * kRing2;             // [2] accumulator half ready
-  uint64_t* a_ready = bars + 2 * kRing2 + 2;        // [2] half drained + its outputs written
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kRing2 + 4);
-
-  const int count = io.count ? min(io.cap, *io.count) : io.cap;
-  const int ntiles = (count + 127) >> 7;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kRing2; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(&d_full[0], 1);
-    mbar_init(&d_full[1], 1);
-    mbar_init(&a_ready[0], NEPI);
-    mbar_init(&a_ready[1], NEPI);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== weight loader =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int s = 0; s < P.nsteps; ++s) {
-          const char* src = (const char*)P.blob + (size_t)P.step[s].slot_off * kSlotBytes;
-          const int nslot = 2 * P.step[s].nk;              // v1 slots of this step: (kc, hi|lo)
-          for (int h = 0; h < 2; ++h) {
-            for (int j = 0; j < nslot; ++j, ++it) {
-              int r = it % kRing2;
-              uint32_t ph = (it / kRing2) & 1;
-              mbar_wait(&empty[r], ph ^ 1);
-              mbar_expect_tx(&full[r], kHalfSlot);
-              bulk_g2s(ring + (size_t)r * kHalfSlot, src + (size_t)j * kSlotBytes + (size_t)h * kHalfSlot, kHalfSlot,
-                       &full[r]);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // N = 128
-      const uint32_t a_hi = smem_u32(A), a_lo = smem_u32(A) + 65536;
-      uint32_t it = 0, ar_ph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int s = 0; s < P.nsteps; ++s) {
-          const int nk = P.step[s].nk;
-          const bool from_tmem = ((s & 1) != 0) && !(io.variant & 1);
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t dcol = tmem + (uint32_t)(128 * h);
-            uint32_t acc = 0;
-            for (int kc = 0; kc < nk; ++kc) {
-              if (h == 0 && kc == 0) {          // D0 drained + K chunks 0,1 of this layer's operand written
-                mbar_wait(&a_ready[0], ar_ph);
-                tc_fence_after();
-              }
-              if (h == 0 && kc == 2) {          // D1 drained + K chunks 2,3 written
-                mbar_wait(&a_ready[1], ar_ph);
-                tc_fence_after();
-              }
-              // hi half-slot: A_hi.W_hi + A_lo.W_hi
-              int r = it % kRing2;
-              mbar_wait(&full[r], (it / kRing2) & 1);
-              tc_fence_after();
-              uint32_t wb = smem_u32(ring + (size_t)r * kHalfSlot);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                uint64_t bd = make_desc(wb + ks * 32);
-                if (from_tmem) {
-                  umma_f16_ts(dcol, tmem + kTHi + (uint32_t)(kc * 32 + ks * 8), bd, idesc, acc);
-                  acc = 1;
-                  umma_f16_ts(dcol, tmem + kTLo + (uint32_t)(kc * 32 + ks * 8), bd, idesc, 1);
-                } else {
-                  umma_f16(dcol, make_desc(a_hi + kc * 16384 + ks * 32), bd, idesc, acc);
-                  acc = 1;
-                  umma_f16(dcol, make_desc(a_lo + kc * 16384 + ks * 32), bd, idesc, 1);
-                }
-              }
-              umma_commit(&empty[r]);
-              ++it;
-              // lo half-slot: A_hi.W_lo
-              r = it % kRing2;
-              mbar_wait(&full[r], (it / kRing2) & 1);
-              tc_fence_after();
-              wb = smem_u32(ring + (size_t)r * kHalfSlot);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (from_tmem)
-                  umma_f16_ts(dcol, tmem + kTHi + (uint32_t)(kc * 32 + ks * 8), make_desc(wb + ks * 32), idesc, 1);
-                else
-                  umma_f16(dcol, make_desc(a_hi + kc * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-              }
-              umma_commit(&empty[r]);
-              ++it;
-            }
-            if (h == 0 && nk <= 2) {            // short layers (the embedding): still consume a_ready[1]
-              mbar_wait(&a_ready[1], ar_ph);
-              tc_fence_after();
-            }
-            umma_commit(&d_full[h]);
-          }
-          ar_ph ^= 1;
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int part = (warp - 2) >> 2;       // column part
-    const int row = q * 32 + lane;
-    const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
-    char* scr = io.scratch + (size_t)blockIdx.x * io.scratch_per_cta;
-    float4* sig = (float4*)scr;                                  // [8][64][128]
-    uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
-    float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
-    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
-    uint32_t df_ph = 0;
-    const int d = P.d_in, E = P.E;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int pt = tile * 128 + row;
-      const bool valid = pt < count;
-      float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (valid)
-        for (int a = 0; a < d; ++a) x[a] = io.x[(size_t)pt * d + a];
-      const int slot = valid ? (io.slot ? io.slot[pt] : pt) : 0;
-      // ---- tile prologue: embedding -> A (K-blocks 0 .. nk0-1), zero padded ----
-      {
-        // positional embedding (embedders.py:8-34): the (frequency, axis) pairs of a row are split over its
-        // column-part threads, one sincosf each, parked in scratch (the `ge` region is free until the reverse
-        // sweep) so that the skip connection of layer 4 re-reads instead of recomputing them
-        const int npair = d * P.multires;
-        for (int pi = part; pi < npair; pi += NPART) {
-          int f = pi / d, a = pi - f * d;
-          float sn, cs;
-          sincosf(__fmul_rn(x[a], (float)(1 << f)), &sn, &cs);
-          ge[(size_t)(d + 2 * f * d + a) * 128 + row] = sn;
-          ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row] = cs;
-        }
-        if (part == 0)
-          for (int a = 0; a < d; ++a) ge[(size_t)a * 128 + row] = x[a];
-        __threadfence_block();
-        ep_bar<NEPI>();
-        const int ncol = P.step[0].nk * 64;
-        const int c0 = part * (ncol / NPART), c1 = c0 + ncol / NPART;
-        for (int c = c0; c < c1; c += 8) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? ge[(size_t)(c + j) * 128 + row] : 0.f;
-          store_a8(A, row, c, v);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(&a_ready[0]);
-        mbar_arrive(&a_ready[1]);
-      }
-      // colour-net extra inputs: foreground [x_c, n] (networks.py:281), background view-dir embedding (:275)
-      float xin[27];
-#pragma unroll
-      for (int e = 0; e < 27; ++e) xin[e] = 0.f;
-      if (io.extra) {
-        float dv[3] = {0.f, 0.f, 0.f};
-        if (valid)
-          for (int a = 0; a < 3; ++a) dv[a] = io.extra[(size_t)pt * 3 + a];
-        for (int e = 0; e < 27; ++e) xin[e] = embed_elem(dv, 3, e);
-      } else {
-        xin[0] = x[0];
-        xin[1] = x[1];
-        xin[2] = x[2];
-      }
-      for (int s = 0; s < P.nsteps; ++s) {
-        const TcStep st = P.step[s];
-        const float isc = P.inv_scale[st.sc];
-        const bool to_tmem = (((s + 1) & 1) != 0) && !(io.variant & 1);   // where the next layer reads its operand from
-        const bool late = ((st.flags & (F_SEED_BWD | F_FINAL_GRAD)) != 0) || (io.variant & 2);   // tails rewrite the operand
-        if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
-        float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
-        float va[CW];
-        auto process_chunk = [&](float* v, float* vnext, const int c) {
-          float4 s4[G4];
-          const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
-          if (need_sig) {   // issue the sigma' loads before waiting on TMEM: they are the long-latency part
-#pragma unroll
-            for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row];
-          }
-          tmem_wait<CW>(v);
-          if (st.epi == EPI_SOFTPLUS) {
-            float4 b4[G4];
-#pragma unroll
-            for (int g4 = 0; g4 < G4; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
-            if (st.flags & F_SAVE_SIG) {
-#pragma unroll
-              for (int g4 = 0; g4 < G4; ++g4) {
-                float dd[4];
-                softplus_fast_grad(fmaf(v[4 * g4 + 0], isc, b4[g4].x), v[4 * g4 + 0], dd[0]);
-                softplus_fast_grad(fmaf(v[4 * g4 + 1], isc, b4[g4].y), v[4 * g4 + 1], dd[1]);
-                softplus_fast_grad(fmaf(v[4 * g4 + 2], isc, b4[g4].z), v[4 * g4 + 2], dd[2]);
-                softplus_fast_grad(fmaf(v[4 * g4 + 3], isc, b4[g4].w), v[4 * g4 + 3], dd[3]);
-                sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row] = make_float4(dd[0], dd[1], dd[2], dd[3]);
-              }
-            } else {
-#pragma unroll
-              for (int g4 = 0; g4 < G4; ++g4) {
-                v[4 * g4 + 0] = softplus_fast(fmaf(v[4 * g4 + 0], isc, b4[g4].x));
-                v[4 * g4 + 1] = softplus_fast(fmaf(v[4 * g4 + 1], isc, b4[g4].y));
-                v[4 * g4 + 2] = softplus_fast(fmaf(v[4 * g4 + 2], isc, b4[g4].z));
-                v[4 * g4 + 3] = softplus_fast(fmaf(v[4 * g4 + 3], isc, b4[g4].w));
-              }
-            }
-            if ((st.flags & F_INJECT_EMB) && c + CW > P.inj_col) {
-#pragma unroll
-              for (int j = 0; j < CW; ++j)
-                if (c + j >= P.inj_col) v[j] = ge[(size_t)(c + j - P.inj_col) * 128 + row];
-            }
-            if (st.flags & F_SDF_DOT) {
-#pragma unroll
-              for (int g4 = 0; g4 < G4; ++g4) {
-                float4 w4 = __ldg((const float4*)(P.w8row + c + 4 * g4));
-                dot0 = fmaf(v[4 * g4 + 0], w4.x, dot0);
-                dot0 = fmaf(v[4 * g4 + 1], w4.y, dot0);
-                dot0 = fmaf(v[4 * g4 + 2], w4.z, dot0);
-                dot0 = fmaf(v[4 * g4 + 3], w4.w, dot0);
-              }
-            }
-          } else if (st.epi == EPI_FEAT) {
-#pragma unroll
-            for (int g4 = 0; g4 < G4; ++g4) {
-              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
-              v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
-              v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
-              v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
-              v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
-            }
-            if ((st.flags & F_FEAT_OUT) && io.feat_out && valid) {
-#pragma unroll
-              for (int j = 0; j < CW; j += 4)
-                *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else if (st.epi == EPI_BWD) {
-            if (st.flags & F_FINAL_GRAD) {
-              // d / d embed of layer 0 (first E columns matter): add to the parked skip gradient
-              if (c < 128) {
-#pragma unroll
-                for (int j = 0; j < CW; ++j)
-                  if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j] * isc;
-              }
-            } else if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
-              // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
-              const float* s4f = reinterpret_cast<const float*>(s4);
-#pragma unroll
-              for (int j = 0; j < CW; ++j) {
-                float gval = v[j] * isc;
-                if (c + j >= P.inj_col) {
-                  ge[(size_t)(c + j - P.inj_col) * 128 + row] = gval;
-                  v[j] = 0.f;
-                } else {
-                  v[j] = gval * s4f[j];
-                }
-              }
-            } else {
-#pragma unroll
-              for (int g4 = 0; g4 < G4; ++g4) {
-                v[4 * g4 + 0] *= isc * s4[g4].x;
-                v[4 * g4 + 1] *= isc * s4[g4].y;
-                v[4 * g4 + 2] *= isc * s4[g4].z;
-                v[4 * g4 + 3] *= isc * s4[g4].w;
-              }
-            }
-          } else {   // EPI_RELU
-#pragma unroll
-            for (int g4 = 0; g4 < G4; ++g4) {
-              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
-              v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
-              v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
-              v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
-              v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
-            }
-            if (st.flags & F_EXTRA_IN) {
-              for (int e = 0; e < P.n_extra; ++e) {
-                const float xe = xin[e];
-                const float4* w4 = (const float4*)(P.W0x + e * 256 + c);
-#pragma unroll
-                for (int j4 = 0; j4 < G4; ++j4) {
-                  float4 ww = __ldg(w4 + j4);
-                  v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
-                  v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
-                  v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
-                  v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
-            if (st.flags & F_RGB_OUT) {
-#pragma unroll
-              for (int g4 = 0; g4 < G4; ++g4) {
-                float4 w0 = __ldg((const float4*)(P.Wrgb + c + 4 * g4));
-                float4 w1 = __ldg((const float4*)(P.Wrgb + 256 + c + 4 * g4));
-                float4 w2 = __ldg((const float4*)(P.Wrgb + 512 + c + 4 * g4));
-                dot0 = fmaf(v[4 * g4 + 0], w0.x, fmaf(v[4 * g4 + 1], w0.y, fmaf(v[4 * g4 + 2], w0.z, fmaf(v[4 * g4 + 3], w0.w, dot0))));
-                dot1 = fmaf(v[4 * g4 + 0], w1.x, fmaf(v[4 * g4 + 1], w1.y, fmaf(v[4 * g4 + 2], w1.z, fmaf(v[4 * g4 + 3], w1.w, dot1))));
-                dot2 = fmaf(v[4 * g4 + 0], w2.x, fmaf(v[4 * g4 + 1], w2.y, fmaf(v[4 * g4 + 2], w2.z, fmaf(v[4 * g4 + 3], w2.w, dot2))));
-              }
-            }
-          }
-          // activations of this chunk -> A (fp16 hi/lo, swizzled) unless this is the last layer
-          if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
-#pragma unroll
-            for (int j = 0; j < CW; j += 8) store_out8(to_tmem, A, t_row, row, c + j, v + j);
-            if (st.flags & F_STASH_FEAT) {
-              // stash the feature chunks (they come back as the colour net's input)
-#pragma unroll
-              for (int j = 0; j < CW; j += 8) {
-                uint4 hi, lo;
-                split8(v + j, hi, lo);
-                int chunk = (c + j) >> 3;
-                fsc[(size_t)chunk * 128 + row] = hi;
-                fsc[(size_t)(32 + chunk) * 128 + row] = lo;
-              }
-            }
-          }
-        };
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&d_full[h], df_ph);
-          tc_fence_after();
-          const int cbeg = 128 * h + part * PCOLS, cend = cbeg + PCOLS;
-          for (int c = cbeg; c < cend; c += CW) {
-            tmem_issue<CW>(t_row + (uint32_t)c, va);
-            process_chunk(va, va, c);
-          }
-          if (!late && s + 1 < P.nsteps) {
-            // half h drained and its outputs (K columns 128h..128h+127 of the next operand) written
-            if (to_tmem) tmem_st_wait(); else fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(&a_ready[h]);
-          }
-        }
-        df_ph ^= 1;
-        tc_fence_before();
-        // ---- step-specific tails ----
-        if (st.flags & F_SDF_DOT) {
-          misc[row * 32 + part] = dot0;
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (part == 0 && valid && io.sdf_out) {
-            float sacc = __ldg(P.b8);
-#pragma unroll
-            for (int pp = 0; pp < NPART; ++pp) sacc += misc[row * 32 + pp];
-            io.sdf_out[slot] = sacc;
-          }
-          ep_bar<NEPI>();
-        }
-        if (st.flags & F_SEED_BWD) {
-          // operand of the reverse sweep = W8[0,:] * sigma'_7    (d sdf / d z7)
-          for (int h = 0; h < 2; ++h) {
-            const int cbeg = 128 * h + part * PCOLS, cend = cbeg + PCOLS;
-            for (int c = cbeg; c < cend; c += 8) {
-              float4 s0 = sig[((size_t)7 * 64 + (c >> 2)) * 128 + row];
-              float4 s1 = sig[((size_t)7 * 64 + (c >> 2) + 1) * 128 + row];
-              float4 wa = __ldg((const float4*)(P.w8row + c));
-              float4 wb = __ldg((const float4*)(P.w8row + c + 4));
-              float v[8] = {s0.x * wa.x, s0.y * wa.y, s0.z * wa.z, s0.w * wa.w,
-                            s1.x * wb.x, s1.y * wb.y, s1.z * wb.z, s1.w * wb.w};
-              store_out8(to_tmem, A, t_row, row, c, v);
-            }
-          }
-        }
-        if (st.flags & F_SKIP_GRAD) __threadfence_block();
-        if (st.flags & F_FINAL_GRAD) {
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (part == 0) {
-            // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos)
-            float g[3] = {0.f, 0.f, 0.f};
-            for (int a = 0; a < d && a < 3; ++a) {
-              float acc = ge[(size_t)a * 128 + row];
-              for (int f = 0; f < P.multires; ++f) {
-                float fr = (float)(1 << f);
-                float t = __fmul_rn(x[a], fr);
-                float sn, cs;
-                sincosf(t, &sn, &cs);
-                float gs = ge[(size_t)(d + 2 * f * d + a) * 128 + row];
-                float gc = ge[(size_t)(d + (2 * f + 1) * d + a) * 128 + row];
-                acc += fr * (cs * gs - sn * gc);
-              }
-              g[a] = acc;
-            }
-            if (io.grad_out && valid) {
-              io.grad_out[3 * (size_t)pt] = g[0];
-              io.grad_out[3 * (size_t)pt + 1] = g[1];
-              io.grad_out[3 * (size_t)pt + 2] = g[2];
-            }
-            float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-            if (io.jinv && valid) {
-              const float* J = io.jinv + 12 * (size_t)pt;
-              float v0 = g[0] * J[0] + g[1] * J[3] + g[2] * J[6];
-              float v1 = g[0] * J[1] + g[1] * J[4] + g[2] * J[7];
-              float v2 = g[0] * J[2] + g[1] * J[5] + g[2] * J[8];
-              float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
-              v0 /= nr; v1 /= nr; v2 /= nr;
-              float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
-              n0 = v0 / n2r; n1 = v1 / n2r; n2 = v2 / n2r;
-              if (io.nrm_out) {
-                io.nrm_out[3 * (size_t)slot] = n0;
-                io.nrm_out[3 * (size_t)slot + 1] = n1;
-                io.nrm_out[3 * (size_t)slot + 2] = n2;
-              }
-            }
-            misc[row * 32 + 4] = n0;
-            misc[row * 32 + 5] = n1;
-            misc[row * 32 + 6] = n2;
-          }
-          __threadfence_block();
-          ep_bar<NEPI>();
-          xin[3] = misc[row * 32 + 4];
-          xin[4] = misc[row * 32 + 5];
-          xin[5] = misc[row * 32 + 6];
-          // features back into A for the colour net
-          if (s + 1 < P.nsteps) {
-            for (int h = 0; h < 2; ++h) {
-              const int cbeg = 128 * h + part * PCOLS, cend = cbeg + PCOLS;
-              for (int c = cbeg; c < cend; c += 8) {
-                int chunk = c >> 3;
-                uint4 hi = fsc[(size_t)chunk * 128 + row];
-                uint4 lo = fsc[(size_t)(32 + chunk) * 128 + row];
-                if (to_tmem) {
-                  tmem_st4(t_row + kTHi + (uint32_t)(c >> 1), hi);
-                  tmem_st4(t_row + kTLo + (uint32_t)(c >> 1), lo);
-                } else {
-                  uint32_t o = a_off(row, c >> 6, chunk & 7);
-                  *reinterpret_cast<uint4*>(A + o) = hi;
-                  *reinterpret_cast<uint4*>(A + 65536 + o) = lo;
-                }
-              }
-            }
-          }
-        }
-        if (st.flags & F_RGB_OUT) {
-          misc[row * 32 + 8 + part * 3 + 0] = dot0;
-          misc[row * 32 + 8 + part * 3 + 1] = dot1;
-          misc[row * 32 + 8 + part * 3 + 2] = dot2;
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (part == 0 && valid && io.rgb_out) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              float z = __ldg(P.brgb + k);
-#pragma unroll
-              for (int pp = 0; pp < NPART; ++pp) z += misc[row * 32 + 8 + pp * 3 + k];
-              io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
-            }
-          }
-          ep_bar<NEPI>();
-        }
-        // hand A (and the drained accumulator) to the MMA warp for the next step of this tile;
-        // the last step's hand-over is the next tile's prologue arrival
-        if (late && s + 1 < P.nsteps) {
-          if (to_tmem) tmem_st_wait(); else fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(&a_ready[0]);
-          mbar_arrive(&a_ready[1]);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -1700,27 +1183,14 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
              ws_bytes, (size_t)grid * kScratchPerCta);
   io.scratch = (char*)ws;
   io.scratch_per_cta = kScratchPerCta;
-  {
-    static int variant = -1;
-    if (variant < 0) {
-      const char* ev = getenv("MP_TC_VARIANT");
-      variant = ev ? atoi(ev) : 0;
-    }
-    io.variant = variant;
-  }
   static bool attr_set = false;
   static int nw = 16;
   static int pipe = 1; // K-block-granular hand-over with two accumulators (MP_TC_PIPE=0: whole-layer hand-over)
-  static int v2 = 0;   // overlapped TS-mode variant: correct (all parity tests) but measured 6 % slower, see profiles/
   if (!attr_set) {
     const char* e = getenv("MP_TC_EPI_WARPS");
     if (e && atoi(e) == 8) nw = 8;
-    const char* e2 = getenv("MP_TC_V2");
-    if (e2) v2 = atoi(e2);
-    if (nw != 16) v2 = 0;
     const char* e3 = getenv("MP_TC_PIPE");
     if (e3) pipe = atoi(e3);
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel_v2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -1740,9 +1210,7 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
     }
     MP_CHECK_CUDA(cudaEventRecord(pe.e0, st));
   }
-  if (v2)
-    tc_chain_kernel_v2<16><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
-  else if (nw == 16 && pipe)
+  if (nw == 16 && pipe)
     tc_chain_kernel<16, true><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
   else if (nw == 16)
     tc_chain_kernel<16, false><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
