@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes);   // [96][128]
     uint32_t df_ph = 0;
     const int d = P.d_in, E = P.E;
-    const int cbeg = part * PCOLS, cend = cbeg + PCOLS;
+    const int cbeg = part * PCOLS;
     constexpr int NCH = PCOLS / CW;          // chunks per thread and step
     // first column of this thread's i-th chunk: contiguous, or 16 columns of every K-block in K order (PIPE)
     auto col_of = [&](int i) { return PIPE ? i * 64 + part * CW : cbeg + i * CW; };
@@ -522,17 +522,61 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         const uint32_t t_row = t_row0 + (PIPE ? ebuf * 256u : 0u);
         ebuf ^= 1;
         // steps whose operand for the next step is complete chunk by chunk (no tail rewrites A)
-        const bool chunk_handover = PIPE && s + 1 < P.nsteps && !(st.flags & (F_RGB_OUT | F_FINAL_GRAD | F_SEED_BWD));
+        const bool chunk_handover = PIPE && s + 1 < P.nsteps && !(st.flags & (F_RGB_OUT | F_FINAL_GRAD));
         if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
         float va[CW];
+        // the accumulator registers are dead once a chunk has been split to fp16: the next chunk's TMEM load is
+        // started there, so its latency hides behind this chunk's stores and hand-over
+        auto issue_next = [&](const int ci) {
+          if (ci + 1 < NCH) tmem_issue<CW>(t_row + (uint32_t)col_of(ci + 1), va);
+        };
         auto process_chunk = [&](float* v, const int ci) {
           const int c = col_of(ci);
-          tmem_wait<CW>(v);
-          if (st.epi == EPI_SOFTPLUS) {
-            float4 b4[G4];
+          // the bias of this chunk is fetched under the TMEM load
+          float4 b4[G4];
+          if (st.bias) {
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
+          }
+          tmem_wait<CW>(v);
+          if (st.epi == EPI_SOFTPLUS) {
+            if ((st.flags & (F_SAVE_SIG | F_SEED_BWD)) == (F_SAVE_SIG | F_SEED_BWD)) {
+              // last SDF layer of the fused chain: sigma'_7 is consumed right here -- the reverse sweep starts from
+              // A = W8[0,:] * sigma'_7 (d sdf / d z7), h7 only feeds the sdf dot and the feature stash
+              float seed[CW];
+#pragma unroll
+              for (int g4 = 0; g4 < G4; ++g4) {
+                float4 w4 = __ldg((const float4*)(P.w8row + c + 4 * g4));
+                float dd[4];
+                softplus_fast_grad(fmaf(v[4 * g4 + 0], isc, b4[g4].x), v[4 * g4 + 0], dd[0]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 1], isc, b4[g4].y), v[4 * g4 + 1], dd[1]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 2], isc, b4[g4].z), v[4 * g4 + 2], dd[2]);
+                softplus_fast_grad(fmaf(v[4 * g4 + 3], isc, b4[g4].w), v[4 * g4 + 3], dd[3]);
+                seed[4 * g4 + 0] = dd[0] * w4.x;
+                seed[4 * g4 + 1] = dd[1] * w4.y;
+                seed[4 * g4 + 2] = dd[2] * w4.z;
+                seed[4 * g4 + 3] = dd[3] * w4.w;
+                dot0 = fmaf(v[4 * g4 + 0], w4.x, dot0);
+                dot0 = fmaf(v[4 * g4 + 1], w4.y, dot0);
+                dot0 = fmaf(v[4 * g4 + 2], w4.z, dot0);
+                dot0 = fmaf(v[4 * g4 + 3], w4.w, dot0);
+              }
+              uint4 fh[CW / 8], fl[CW / 8];
+#pragma unroll
+              for (int j = 0; j < CW; j += 8) split8(v + j, fh[j >> 3], fl[j >> 3]);
+              issue_next(ci);
+#pragma unroll
+              for (int j = 0; j < CW; j += 8) {
+                if (st.flags & F_STASH_FEAT) {
+                  int chunk = (c + j) >> 3;
+                  fsc[(size_t)chunk * 128 + row] = fh[j >> 3];
+                  fsc[(size_t)(32 + chunk) * 128 + row] = fl[j >> 3];
+                }
+                store_a8(A, row, c + j, seed + j);
+              }
+              return;
+            }
             if (st.flags & F_SAVE_SIG) {
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4) {
@@ -570,7 +614,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           } else if (st.epi == EPI_FEAT) {
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) {
-              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
+              const float4 b = b4[g4];
               v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
               v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
               v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
@@ -619,7 +663,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           } else {   // EPI_RELU
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) {
-              float4 b = __ldg((const float4*)(st.bias + c + 4 * g4));
+              const float4 b = b4[g4];
               v[4 * g4 + 0] = fmaf(v[4 * g4 + 0], isc, b.x);
               v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
               v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
@@ -660,25 +704,30 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           }
           // activations of this chunk -> A (fp16 hi/lo, swizzled) unless this is the last layer
           if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
+            uint4 hi[CW / 8], lo[CW / 8];
 #pragma unroll
-            for (int j = 0; j < CW; j += 8) store_a8(A, row, c + j, v + j);
-            if (st.flags & F_STASH_FEAT) {
-              // stash the feature chunks (they come back as the colour net's input)
+            for (int j = 0; j < CW; j += 8) split8(v + j, hi[j >> 3], lo[j >> 3]);
+            issue_next(ci);
 #pragma unroll
-              for (int j = 0; j < CW; j += 8) {
-                uint4 hi, lo;
-                split8(v + j, hi, lo);
+            for (int j = 0; j < CW; j += 8) {
+              const uint32_t o = a_off(row, (c + j) >> 6, ((c + j) >> 3) & 7);
+              *reinterpret_cast<uint4*>(A + o) = hi[j >> 3];
+              *reinterpret_cast<uint4*>(A + 65536 + o) = lo[j >> 3];
+              if (st.flags & F_STASH_FEAT) {
+                // stash the feature chunks (they come back as the colour net's input)
                 int chunk = (c + j) >> 3;
-                fsc[(size_t)chunk * 128 + row] = hi;
-                fsc[(size_t)(32 + chunk) * 128 + row] = lo;
+                fsc[(size_t)chunk * 128 + row] = hi[j >> 3];
+                fsc[(size_t)(32 + chunk) * 128 + row] = lo[j >> 3];
               }
             }
+          } else {
+            issue_next(ci);
           }
         };
-        // (double-buffering the TMEM reads was measured slower: +20 % kernel time from spills / code size)
+        // (a second register buffer for the TMEM reads was measured slower: +20 % kernel time from spills / code size)
+        tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
 #pragma unroll 1
         for (int ci = 0; ci < NCH; ++ci) {
-          tmem_issue<CW>(t_row + (uint32_t)col_of(ci), va);
           process_chunk(va, ci);
           if (chunk_handover) {
             // K-block ci of the next layer's operand is complete in this thread
@@ -700,18 +749,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             io.sdf_out[slot] = sacc;
           }
           ep_bar<NEPI>();
-        }
-        if (st.flags & F_SEED_BWD) {
-          // A = W8[0,:] * sigma'_7    (d sdf / d z7)
-          for (int c = cbeg; c < cend; c += 8) {
-            float4 s0 = sig[((size_t)7 * 64 + (c >> 2)) * 128 + row];
-            float4 s1 = sig[((size_t)7 * 64 + (c >> 2) + 1) * 128 + row];
-            float4 wa = __ldg((const float4*)(P.w8row + c));
-            float4 wb = __ldg((const float4*)(P.w8row + c + 4));
-            float v[8] = {s0.x * wa.x, s0.y * wa.y, s0.z * wa.z, s0.w * wa.w,
-                          s1.x * wb.x, s1.y * wb.y, s1.z * wb.z, s1.w * wb.w};
-            store_a8(A, row, c, v);
-          }
         }
         if (st.flags & F_SKIP_GRAD) __threadfence_block();
         if (st.flags & F_FINAL_GRAD) {
