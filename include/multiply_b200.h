@@ -99,6 +99,10 @@ int mp_get_engine(void);
  * on the recorded events and returns summed milliseconds, launch counts and processed points (host arrays of 4). */
 int mp_profile_enable(int on);
 int mp_profile_read(double* ms_host, long long* launches_host, double* points_host, int reset);
+/* Diagnostics: cycle stamps of one tile of CTA 0 of the last tcgen05 launch (recorded when MP_TC_KNOBS has bit 1 set):
+ * out[s*8 + 0..6] epilogue warp (step start, accumulator ready, chunk 0..3 done, step end), out[2048 + s*8 + 0..4] MMA
+ * issuer (operand K-block 0..3 ready, commit).  scripts/gpu_trace.py prints them. */
+int mp_tc_trace_read(unsigned long long* out, int n);
 
 /* ImplicitNet.forward (networks.py:126-208): x [N,d_in] -> out [N,257] (sdf | feature).
  * sdf / feat may be NULL.  Replaces `self.foreground_implicit_network_list[p](x_c, cond)`. */

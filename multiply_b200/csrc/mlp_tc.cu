@@ -33,7 +33,8 @@ enum {
   F_SEED_BWD = 8,      // after this step: A = W8[0,:] * sigma'_7 (start of the reverse sweep)
   F_SKIP_GRAD = 16,    // reverse sweep: columns >= inj_col are d/d embed of the skip; park them, zero A there
   F_FINAL_GRAD = 32,   // reverse sweep end: d sdf / d x -> normal ; then reload the features into A
-  F_EXTRA_IN = 64,     // colour layer 0: add W0[:, :n_extra] . extra inputs
+  F_EXTRA_IN = 64,     // colour layer 0: a fifth K-block carries the extra inputs ([x_c, n] or the view embedding): they are
+                       // staged into A's K-block 0 once its MMAs have drained, and accumulate into the same tile
   F_RGB_OUT = 128,     // last colour layer: rgb = sigmoid(h . Wrgb^T + b)
   F_FEAT_OUT = 256,    // write the fp32 features to feat_out (operator API)
   F_STASH_FEAT = 512   // park the feature chunks in scratch (they return as the colour net's input after the reverse sweep)
@@ -43,7 +44,7 @@ constexpr int kSlotBytes = 32768;          // 256 rows x 64 fp16
 constexpr int kRing = 3;
 
 struct TcStep {
-  int nk;               // 64-wide K chunks of A consumed by this layer
+  int nk;               // 64-wide K chunks of A consumed by this layer (5 with F_EXTRA_IN: the last one re-uses K-block 0)
   int epi;
   int flags;
   int sig;              // sigma' scratch layer (save: forward, load: reverse) or -1
@@ -63,7 +64,6 @@ struct TcProgram {
   int d_in, multires, E, inj_col, n_extra, col_n;   // col_n: width of the colour hidden layers
   const float* w8row;    // W8[0,:]  [256]
   const float* b8;       // b8[0]
-  const float* W0x;      // colour layer 0, extra-input columns, transposed [n_extra][256]
   const float* Wrgb;     // [3][256]
   const float* brgb;     // [3]
 };
@@ -80,6 +80,7 @@ struct TcIO {
   float* nrm_out;        // [slots,3]
   float* grad_out;       // [cap,3] dense or nullptr
   float* feat_out;       // [cap,256] dense or nullptr
+  int knobs;             // experiment switches (MP_TC_KNOBS bit mask), 0 in production
   char* scratch;         // per-CTA scratch
   size_t scratch_per_cta;
 };
@@ -90,7 +91,8 @@ constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo c
 constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
 constexpr size_t kMiscBytes = (size_t)128 * 32 * 4;          // partial sums / normals [128][32]
 constexpr size_t kEmbBytes = (size_t)96 * 128 * 4;           // input embedding of the tile [E<=96][128]
-constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes;
+constexpr size_t kGe2Bytes = (size_t)96 * 128 * 4;           // d sdf / d embed through layer 0 [E<=96][128]
+constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes + kGe2Bytes;
 
 // shared memory carve-up
 constexpr int kABytes = 2 * 4 * 128 * 128;                   // hi + lo, 4 K-blocks of [128 x 128B]
@@ -122,6 +124,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// bounded variant for the timing-experiment lanes (may lag more than one phase behind: never spin forever)
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int max_tries) {
+  for (int i = 0; i < max_tries; ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -206,6 +224,26 @@ __device__ __forceinline__ float embed_elem(const float* x, int d, int k) {
   int f = (k - d) / (2 * d), r = (k - d) - f * 2 * d;
   float t = __fmul_rn(x[r < d ? r : r - d], (float)(1 << f));
   return r < d ? sinf(t) : cosf(t);
+}
+
+// The per-CTA scratch (sigma', stashed features) streams: it is written once and read once per tile.  L2-only
+// accesses keep it out of the small L1 that is left beside 224 KB of shared memory, so that the read-only vectors
+// every chunk needs (bias, W8 row, extra-input and rgb weights) stay L1-resident.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 template <int N>
@@ -303,6 +341,9 @@ __device__ __forceinline__ void tmem_wait<32>(float* v) {
                : "memory");
 }
 
+// cycle stamps of CTA 0 (MP_TC_KNOBS bit 1): [0..] epilogue warp 2, [2048..] MMA issuer; see mp_tc_trace_read
+__device__ unsigned long long g_trace[4096];
+
 // NW epilogue warps (8 or 16): warp w owns TMEM lane quadrant w % 4 (rows) and column part (w-2)/4.
 //
 // PIPE (NW = 16 only): K-block-granular hand-over between the epilogue and the MMA issuer.
@@ -335,7 +376,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   uint64_t* empty = bars + kRing;                   // [kRing]
   uint64_t* d_full = bars + 2 * kRing;
   uint64_t* a_ready = bars + 2 * kRing + 1;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kRing + 1 + NBAR);
+  uint64_t* x_free = bars + 2 * kRing + 1 + NBAR;      // K-block 0 of A drained by the MMAs (extra-input steps)
+  uint64_t* x_ready = x_free + 1;                      // extra inputs staged there
+  uint32_t* tmem_slot = (uint32_t*)(x_ready + 1);
 
   const int count = io.count ? min(io.cap, *io.count) : io.cap;
   const int ntiles = (count + 127) >> 7;
@@ -347,6 +390,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     }
     mbar_init(d_full, 1);
     for (int i = 0; i < NBAR; ++i) mbar_init(&a_ready[i], NEPI);
+    mbar_init(x_free, 1);
+    mbar_init(x_ready, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -372,18 +417,45 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             int r = it % kRing;
             uint32_t ph = (it / kRing) & 1;
             mbar_wait(&empty[r], ph ^ 1);
-            mbar_expect_tx(&full[r], kSlotBytes);
+            const bool twice = io.knobs & 4;   // timing experiment: fetch every slot twice (same result, 2x weight traffic)
+            mbar_expect_tx(&full[r], twice ? 2 * kSlotBytes : kSlotBytes);
             bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)j * kSlotBytes, kSlotBytes, &full[r]);
+            if (twice) bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)j * kSlotBytes, kSlotBytes, &full[r]);
           }
         }
       }
+    }
+    else if (io.knobs & 8) {
+      // timing experiment: lanes 1..31 shadow the loader and pull one more slot's worth of (other) weights through L2
+      // per ring refill with plain L2 loads (results unchanged, ~2x weight traffic, no request merging)
+      uint32_t it = 0;
+      unsigned acc = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = 0; s < P.nsteps; ++s) {
+          const int nslot = 2 * P.step[s].nk;
+          for (int j = 0; j < nslot; ++j, ++it) {
+            int r = it % kRing;
+            uint32_t ph = (it / kRing) & 1;
+            mbar_wait_bounded(&empty[r], ph ^ 1, 64);
+            const int other = (P.step[s].slot_off + j + P.slots_per_tile / 2) % P.slots_per_tile;
+            const uint4* q = (const uint4*)((const char*)P.blob + (size_t)other * kSlotBytes) + (lane - 1) * 66;
+#pragma unroll 11
+            for (int k = 0; k < 66; ++k) {
+              uint4 w;
+              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q + k));
+              acc ^= w.x ^ w.y ^ w.z ^ w.w;
+            }
+          }
+        }
+      }
+      if (acc == 0x12345679u) g_trace[4095] = acc;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
       const uint32_t a_hi = smem_u32(A), a_lo = smem_u32(A) + 65536;
-      uint32_t it = 0, ar_ph = 0, buf = 0;
+      uint32_t it = 0, ar_ph = 0, buf = 0, xr_ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int s = 0; s < P.nsteps; ++s) {
           if (!PIPE) {
@@ -394,9 +466,15 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           const uint32_t tmem = tmem0 + (PIPE ? buf * 256u : 0u);
           uint32_t acc = 0;
           for (int kc = 0; kc < nk; ++kc) {
-            if (PIPE) {
+            if (kc == 4) {
+              // extra-input K-block: lives where K-block 0 was
+              mbar_wait(x_ready, xr_ph);
+              xr_ph ^= 1;
+              tc_fence_after();
+            } else if (PIPE) {
               mbar_wait(&a_ready[kc], ar_ph);
               tc_fence_after();
+              if ((io.knobs & 2) && blockIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x)) g_trace[2048 + (P.nsteps > 12 ? 0 : 1024) + s * 8 + kc] = clock64();
             }
             // hi slot: A_hi.W_hi + A_lo.W_hi
             int r = it % kRing;
@@ -406,9 +484,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               uint64_t bd = make_desc(wb + ks * 32);
-              umma_f16(tmem, make_desc(a_hi + kc * 16384 + ks * 32), bd, idesc, acc);
+              umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), bd, idesc, acc);
               acc = 1;
-              umma_f16(tmem, make_desc(a_lo + kc * 16384 + ks * 32), bd, idesc, 1);
+              umma_f16(tmem, make_desc(a_lo + (kc & 3) * 16384 + ks * 32), bd, idesc, 1);
             }
             umma_commit(&empty[r]);
             ++it;
@@ -419,14 +497,16 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             wb = smem_u32(ring + (size_t)r * kSlotBytes);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_f16(tmem, make_desc(a_hi + kc * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+              umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
             umma_commit(&empty[r]);
             ++it;
+            if (kc == 0 && nk == 5) umma_commit(x_free);   // K-block 0 may be overwritten once these have completed
           }
           umma_commit(d_full);
+          if ((io.knobs & 2) && blockIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x)) g_trace[2048 + (P.nsteps > 12 ? 0 : 1024) + s * 8 + 4] = clock64();
           if (PIPE) {
             // keep the phases of the unused K-block barriers in step
-            for (int kc = nk; kc < 4; ++kc) mbar_wait(&a_ready[kc], ar_ph);
+            for (int kc = nk < 4 ? nk : 4; kc < 4; ++kc) mbar_wait(&a_ready[kc], ar_ph);
             buf ^= 1;
           }
           ar_ph ^= 1;
@@ -446,7 +526,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
     float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
     float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes);   // [96][128]
-    uint32_t df_ph = 0;
+    float* ge2 = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes);   // [96][128]
+    uint32_t df_ph = 0, xf_ph = 0;
     const int d = P.d_in, E = P.E;
     const int cbeg = part * PCOLS;
     constexpr int NCH = PCOLS / CW;          // chunks per thread and step
@@ -480,6 +561,22 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         }
         if (part == 0)
           for (int a = 0; a < d; ++a) emb[(size_t)a * 128 + row] = x[a];
+        if (io.extra) {
+          // background: embedding of the view direction (n_extra = 3 + 6 * frequencies values), same split
+          float dv[3] = {0.f, 0.f, 0.f};
+          if (valid)
+            for (int a = 0; a < 3; ++a) dv[a] = io.extra[(size_t)pt * 3 + a];
+          const int nvp = (P.n_extra - 3) / 2;
+          for (int pi = part; pi < nvp; pi += NPART) {
+            int f = pi / 3, a = pi - f * 3;
+            float sn, cs;
+            sincosf(__fmul_rn(dv[a], (float)(1 << f)), &sn, &cs);
+            ge[(size_t)(3 + 6 * f + a) * 128 + row] = sn;
+            ge[(size_t)(3 + 6 * f + 3 + a) * 128 + row] = cs;
+          }
+          if (part == 0)
+            for (int a = 0; a < 3; ++a) ge[(size_t)a * 128 + row] = dv[a];
+        }
         __threadfence_block();
         ep_bar<NEPI>();
         const int ncol = P.step[0].nk * 64;
@@ -492,20 +589,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         }
         arrive_all();
       }
-      // colour-net extra inputs: foreground [x_c, n] (networks.py:281), background view-dir embedding (:275)
-      float xin[27];
-#pragma unroll
-      for (int e = 0; e < 27; ++e) xin[e] = 0.f;
-      if (io.extra) {
-        float dv[3] = {0.f, 0.f, 0.f};
-        if (valid)
-          for (int a = 0; a < 3; ++a) dv[a] = io.extra[(size_t)pt * 3 + a];
-        for (int e = 0; e < 27; ++e) xin[e] = embed_elem(dv, 3, e);
-      } else {
-        xin[0] = x[0];
-        xin[1] = x[1];
-        xin[2] = x[2];
-      }
+      // colour-net extra inputs: foreground [x_c, n] (networks.py:281) live in registers (n arrives at the end of the
+      // reverse sweep); the background view-dir embedding (:275) was parked in `ge` by the prologue
+      float nrm[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
         const float isc = P.inv_scale[st.sc];
@@ -514,16 +600,70 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
         if (need_sig) {
 #pragma unroll
-          for (int g4 = 0; g4 < G4; ++g4) s4[g4] = sig[((size_t)st.sig * 64 + ((col_of(0) >> 2) + g4)) * 128 + row];
+          for (int g4 = 0; g4 < G4; ++g4) s4[g4] = ld_stream(&sig[((size_t)st.sig * 64 + ((col_of(0) >> 2) + g4)) * 128 + row]);
         }
+        if (st.nk == 5) {
+          // colour layer 0: once the MMAs over K-block 0 have drained it, this row's extra inputs (16 columns per
+          // column part, zero padded to 64) take its place as the fifth K-block of the same accumulation
+          mbar_wait(x_free, xf_ph);
+          xf_ph ^= 1;
+          constexpr int XC = 64 / NPART;       // columns of the extra K-block staged by each column part
+#pragma unroll
+          for (int c8 = 0; c8 < XC; c8 += 8) {
+            const int e0 = part * XC + c8;
+            float xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = 0.f;
+            if (io.extra) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (e0 + j < P.n_extra) xv[j] = ge[(size_t)(e0 + j) * 128 + row];
+            } else if (e0 == 0) {
+              xv[0] = x[0]; xv[1] = x[1]; xv[2] = x[2];
+              xv[3] = nrm[0]; xv[4] = nrm[1]; xv[5] = nrm[2];
+            }
+            store_a8(A, row, e0, xv);
+          }
+          fence_async_smem();
+          mbar_arrive(x_ready);
+        }
+        const bool tr = (io.knobs & 2) && blockIdx.x == 0 && warp == 2 && lane == 0 && tile == (int)(blockIdx.x + gridDim.x);
+        unsigned long long* trp = g_trace + (P.nsteps > 12 ? 0 : 1024) + s * 8;
+        if (tr) trp[0] = clock64();
         mbar_wait(d_full, df_ph);
         df_ph ^= 1;
         tc_fence_after();
+        if (tr) trp[1] = clock64();
+        auto reload_features = [&]() {
+#pragma unroll
+          for (int c8 = 0; c8 < PCOLS / 8; c8 += 4) {
+            uint4 fh[4], fl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int chunk = (cbeg >> 3) + c8 + u;
+              fh[u] = ld_stream(&fsc[(size_t)chunk * 128 + row]);
+              fl[u] = ld_stream(&fsc[(size_t)(32 + chunk) * 128 + row]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int chunk = (cbeg >> 3) + c8 + u;
+              const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
+              *reinterpret_cast<uint4*>(A + o) = fh[u];
+              *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
+            }
+          }
+          arrive_all();
+        };
+        if (PIPE && (st.flags & F_FINAL_GRAD) && s + 1 < P.nsteps) {
+          // all MMAs of the reverse sweep are done, A is free: the features return for the colour net right away and
+          // its first layer's MMAs run under the rest of this step (the accumulators alternate)
+          reload_features();
+          if (tr) g_trace[512] = clock64();
+        }
         const uint32_t t_row = t_row0 + (PIPE ? ebuf * 256u : 0u);
         ebuf ^= 1;
         // steps whose operand for the next step is complete chunk by chunk (no tail rewrites A)
         const bool chunk_handover = PIPE && s + 1 < P.nsteps && !(st.flags & (F_RGB_OUT | F_FINAL_GRAD));
-        if (st.flags & F_FINAL_GRAD) ep_bar<NEPI>();     // skip-gradient parked by another column part
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;        // sdf / rgb partial dots
         float va[CW];
         // the accumulator registers are dead once a chunk has been split to fp16: the next chunk's TMEM load is
@@ -570,8 +710,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               for (int j = 0; j < CW; j += 8) {
                 if (st.flags & F_STASH_FEAT) {
                   int chunk = (c + j) >> 3;
-                  fsc[(size_t)chunk * 128 + row] = fh[j >> 3];
-                  fsc[(size_t)(32 + chunk) * 128 + row] = fl[j >> 3];
+                  st_stream(&fsc[(size_t)chunk * 128 + row], fh[j >> 3]);
+                  st_stream(&fsc[(size_t)(32 + chunk) * 128 + row], fl[j >> 3]);
                 }
                 store_a8(A, row, c + j, seed + j);
               }
@@ -585,7 +725,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 softplus_fast_grad(fmaf(v[4 * g4 + 1], isc, b4[g4].y), v[4 * g4 + 1], dd[1]);
                 softplus_fast_grad(fmaf(v[4 * g4 + 2], isc, b4[g4].z), v[4 * g4 + 2], dd[2]);
                 softplus_fast_grad(fmaf(v[4 * g4 + 3], isc, b4[g4].w), v[4 * g4 + 3], dd[3]);
-                sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+                st_stream(&sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row], make_float4(dd[0], dd[1], dd[2], dd[3]));
               }
             } else {
 #pragma unroll
@@ -627,11 +767,11 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             }
           } else if (st.epi == EPI_BWD) {
             if (st.flags & F_FINAL_GRAD) {
-              // d / d embed of layer 0 (first E columns matter): add to the parked skip gradient
+              // d / d embed of layer 0 (first E columns matter); the tail adds the parked skip gradient
               if (c < 128) {
 #pragma unroll
                 for (int j = 0; j < CW; ++j)
-                  if (c + j < E) ge[(size_t)(c + j) * 128 + row] += v[j] * isc;
+                  if (c + j < E) ge2[(size_t)(c + j) * 128 + row] = v[j] * isc;
               }
             } else if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
               // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
@@ -658,7 +798,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             if (need_sig && ci + 1 < NCH) {   // next chunk's sigma' streams in behind the stores below
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4)
-                s4[g4] = sig[((size_t)st.sig * 64 + ((col_of(ci + 1) >> 2) + g4)) * 128 + row];
+                s4[g4] = ld_stream(&sig[((size_t)st.sig * 64 + ((col_of(ci + 1) >> 2) + g4)) * 128 + row]);
             }
           } else {   // EPI_RELU
 #pragma unroll
@@ -668,25 +808,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               v[4 * g4 + 1] = fmaf(v[4 * g4 + 1], isc, b.y);
               v[4 * g4 + 2] = fmaf(v[4 * g4 + 2], isc, b.z);
               v[4 * g4 + 3] = fmaf(v[4 * g4 + 3], isc, b.w);
-            }
-            if (st.flags & F_EXTRA_IN) {
-              // n_extra is 6 (foreground) or 27 (background): three inputs per trip keep 12 weight loads in flight
-              for (int e0 = 0; e0 < P.n_extra; e0 += 3) {
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                  const int e = e0 + u;
-                  const float xe = e < P.n_extra ? xin[e] : 0.f;
-                  const float4* w4 = (const float4*)(P.W0x + (e < P.n_extra ? e : 0) * 256 + c);
-#pragma unroll
-                  for (int j4 = 0; j4 < G4; ++j4) {
-                    float4 ww = __ldg(w4 + j4);
-                    v[4 * j4 + 0] = fmaf(ww.x, xe, v[4 * j4 + 0]);
-                    v[4 * j4 + 1] = fmaf(ww.y, xe, v[4 * j4 + 1]);
-                    v[4 * j4 + 2] = fmaf(ww.z, xe, v[4 * j4 + 2]);
-                    v[4 * j4 + 3] = fmaf(ww.w, xe, v[4 * j4 + 3]);
-                  }
-                }
-              }
             }
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -716,8 +837,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               if (st.flags & F_STASH_FEAT) {
                 // stash the feature chunks (they come back as the colour net's input)
                 int chunk = (c + j) >> 3;
-                fsc[(size_t)chunk * 128 + row] = hi[j >> 3];
-                fsc[(size_t)(32 + chunk) * 128 + row] = lo[j >> 3];
+                st_stream(&fsc[(size_t)chunk * 128 + row], hi[j >> 3]);
+                st_stream(&fsc[(size_t)(32 + chunk) * 128 + row], lo[j >> 3]);
               }
             }
           } else {
@@ -729,6 +850,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
 #pragma unroll 1
         for (int ci = 0; ci < NCH; ++ci) {
           process_chunk(va, ci);
+          if (tr) trp[2 + ci] = clock64();
           if (chunk_handover) {
             // K-block ci of the next layer's operand is complete in this thread
             fence_async_smem();
@@ -748,56 +870,67 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             for (int pp = 0; pp < NPART; ++pp) sacc += misc[row * 32 + pp];
             io.sdf_out[slot] = sacc;
           }
-          ep_bar<NEPI>();
+          // (no second barrier: these scratch slots are next written a whole tile -- many barriers -- later)
         }
         if (st.flags & F_SKIP_GRAD) __threadfence_block();
         if (st.flags & F_FINAL_GRAD) {
+          if (tr) g_trace[513] = clock64();
+          // the inverse Jacobian of this row's point (cold: written by the deformer kernel) travels under the barriers
+          float4 ja = make_float4(0.f, 0.f, 0.f, 0.f), jb = ja, jc = ja;
+          if (io.jinv && valid) {
+            const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
+            ja = __ldg(J4);      // J[0..3]
+            jb = __ldg(J4 + 1);  // J[4..7]
+            jc = __ldg(J4 + 2);  // J[8..11]
+          }
           __threadfence_block();
           ep_bar<NEPI>();
+          if (tr) g_trace[514] = clock64();
           // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos).  The (frequency, axis) pairs
           // of a row are split over its column-part threads; sin / cos come back from the prologue's scratch.
+          // Everything here is an L2 round trip (the scratch was written by other warps): batches of five pairs
+          // keep 30 loads in flight instead of six.
           {
             float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
             const int npair = d * P.multires;
-            for (int pi = part; pi < npair; pi += NPART) {
-              const int f = pi / d, a = pi - f * d;
-              const size_t is = (size_t)(d + 2 * f * d + a) * 128 + row, ic = (size_t)(d + (2 * f + 1) * d + a) * 128 + row;
-              const float term = (float)(1 << f) * (emb[ic] * ge[is] - emb[is] * ge[ic]);
-              gp0 += a == 0 ? term : 0.f;
-              gp1 += a == 1 ? term : 0.f;
-              gp2 += a == 2 ? term : 0.f;
+            constexpr int PB = 5;
+            for (int k0 = 0; k0 * NPART + part < npair; k0 += PB) {
+              float es[PB], ec[PB], gs[PB], gc[PB], hs[PB], hc[PB], fr[PB];
+              int ax[PB];
+#pragma unroll
+              for (int u = 0; u < PB; ++u) {
+                int pi = part + (k0 + u) * NPART;
+                const bool ok = pi < npair;
+                pi = ok ? pi : part;
+                const int f = pi / d, a = pi - f * d;
+                const size_t is = (size_t)(d + 2 * f * d + a) * 128 + row, ic = (size_t)(d + (2 * f + 1) * d + a) * 128 + row;
+                es[u] = emb[is]; ec[u] = emb[ic];
+                gs[u] = ge[is];  gc[u] = ge[ic];
+                hs[u] = ge2[is]; hc[u] = ge2[ic];
+                fr[u] = ok ? (float)(1 << f) : 0.f;
+                ax[u] = a;
+              }
+#pragma unroll
+              for (int u = 0; u < PB; ++u) {
+                const float term = fr[u] * (ec[u] * (gs[u] + hs[u]) - es[u] * (gc[u] + hc[u]));
+                gp0 += ax[u] == 0 ? term : 0.f;
+                gp1 += ax[u] == 1 ? term : 0.f;
+                gp2 += ax[u] == 2 ? term : 0.f;
+              }
             }
             if (part == 0) {
-              gp0 += ge[row];
-              if (d > 1) gp1 += ge[128 + row];
-              if (d > 2) gp2 += ge[256 + row];
+              gp0 += ge[row] + ge2[row];
+              if (d > 1) gp1 += ge[128 + row] + ge2[128 + row];
+              if (d > 2) gp2 += ge[256 + row] + ge2[256 + row];
             }
             misc[row * 32 + 20 + part * 3 + 0] = gp0;
             misc[row * 32 + 20 + part * 3 + 1] = gp1;
             misc[row * 32 + 20 + part * 3 + 2] = gp2;
           }
-          // features back into A for the colour net (independent of the gradient: fills the barrier wait)
-          if (s + 1 < P.nsteps) {
-#pragma unroll
-            for (int c8 = 0; c8 < PCOLS / 8; c8 += 4) {
-              uint4 fh[4], fl[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int chunk = (cbeg >> 3) + c8 + u;
-                fh[u] = fsc[(size_t)chunk * 128 + row];
-                fl[u] = fsc[(size_t)(32 + chunk) * 128 + row];
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int chunk = (cbeg >> 3) + c8 + u;
-                const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
-                *reinterpret_cast<uint4*>(A + o) = fh[u];
-                *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
-              }
-            }
-          }
+          if (tr) g_trace[515] = clock64();
           __threadfence_block();
           ep_bar<NEPI>();
+          if (tr) g_trace[516] = clock64();
           float g[3] = {0.f, 0.f, 0.f};
 #pragma unroll
           for (int pp = 0; pp < NPART; ++pp) {
@@ -813,45 +946,53 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           // every column part needs the normal as a colour input: all of them derive it (no second broadcast)
           float n0 = 0.f, n1 = 0.f, n2 = 0.f;
           if (io.jinv && valid) {
-            const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
-            const float4 ja = J4[0], jb = J4[1], jc = J4[2];      // J[0..3], J[4..7], J[8..11]
             float v0 = g[0] * ja.x + g[1] * ja.w + g[2] * jb.z;
             float v1 = g[0] * ja.y + g[1] * jb.x + g[2] * jb.w;
             float v2 = g[0] * ja.z + g[1] * jb.y + g[2] * jc.x;
             float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
-            v0 /= nr; v1 /= nr; v2 /= nr;
+            const float inr = 1.f / nr;
+            v0 *= inr; v1 *= inr; v2 *= inr;
             float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
-            n0 = v0 / n2r; n1 = v1 / n2r; n2 = v2 / n2r;
+            const float in2 = 1.f / n2r;
+            n0 = v0 * in2; n1 = v1 * in2; n2 = v2 * in2;
             if (part == 0 && io.nrm_out) {
               io.nrm_out[3 * (size_t)slot] = n0;
               io.nrm_out[3 * (size_t)slot + 1] = n1;
               io.nrm_out[3 * (size_t)slot + 2] = n2;
             }
           }
-          xin[3] = n0;
-          xin[4] = n1;
-          xin[5] = n2;
+          nrm[0] = n0;
+          nrm[1] = n1;
+          nrm[2] = n2;
+          if (tr) g_trace[517] = clock64();
         }
         if (st.flags & F_RGB_OUT) {
-          misc[row * 32 + 8 + part * 3 + 0] = dot0;
-          misc[row * 32 + 8 + part * 3 + 1] = dot1;
-          misc[row * 32 + 8 + part * 3 + 2] = dot2;
-          __threadfence_block();
+          // last step of the tile: the MMAs are done with A, its K-block 3 serves as the exchange buffer for the
+          // partial dots (the next write there is a whole layer step -- and several barriers -- away)
+          float* xch = reinterpret_cast<float*>(A + 3 * 16384);
+          xch[(part * 3 + 0) * 128 + row] = dot0;
+          xch[(part * 3 + 1) * 128 + row] = dot1;
+          xch[(part * 3 + 2) * 128 + row] = dot2;
           ep_bar<NEPI>();
           if (part == 0 && valid && io.rgb_out) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               float z = __ldg(P.brgb + k);
 #pragma unroll
-              for (int pp = 0; pp < NPART; ++pp) z += misc[row * 32 + 8 + pp * 3 + k];
+              for (int pp = 0; pp < NPART; ++pp) z += xch[(pp * 3 + k) * 128 + row];
               io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
             }
           }
-          ep_bar<NEPI>();
         }
         // hand A (and the drained accumulator) to the MMA warp for the next step of this tile;
         // the last step's hand-over is the next tile's prologue arrival
-        if (s + 1 < P.nsteps && !chunk_handover) arrive_all();
+        if (s + 1 < P.nsteps && !chunk_handover) {
+          if (!(st.flags & F_FINAL_GRAD))
+            arrive_all();
+          else if (!PIPE)
+            reload_features();     // single accumulator: only after this step has drained it
+        }
+        if (tr) trp[6] = clock64();
       }
     }
   }
@@ -927,21 +1068,31 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, int lds, int nrow
   dst[i] = (c < ncols) ? src[(size_t)r * lds + c] : 0.f;
 }
 
-// M[n][k] = sum_j Wc[n][coff + j] * W8f[j][k]   (n < n_rows, k < 256; W8f = W8[1:], row stride ld8)
+// M[n][k] = sum_j Wc[n][coff + j] * W8f[j][k]   (n < n_rows, k < 256; W8f = W8[1:], row stride ld8; M row stride ldm)
 // cb[n]   = sum_j Wc[n][coff + j] * b8f[j]
 __global__ void fold_mm_kernel(const float* __restrict__ Wc, int ldc, int coff, const float* __restrict__ W8f, int ld8,
-                               const float* __restrict__ b8f, int n_rows, float* __restrict__ M, float* __restrict__ cb) {
+                               const float* __restrict__ b8f, int n_rows, float* __restrict__ M, int ldm,
+                               float* __restrict__ cb) {
   int k = blockIdx.x * 16 + threadIdx.x, n = blockIdx.y * 16 + threadIdx.y;
   if (n >= n_rows || k >= 256) return;
   const float* w = Wc + (size_t)n * ldc + coff;
   double acc = 0.0;
   for (int j = 0; j < 256; ++j) acc += (double)w[j] * (double)W8f[(size_t)j * ld8 + k];
-  M[(size_t)n * 256 + k] = (float)acc;
+  M[(size_t)n * ldm + k] = (float)acc;
   if (k == 0) {
     double a2 = 0.0;
     for (int j = 0; j < 256; ++j) a2 += (double)w[j] * (double)b8f[j];
     cb[n] = (float)a2;
   }
+}
+
+// columns 256 .. 319 of the combined colour layer 0: M[n][256 + e] = Wc0[n][e] for the extra inputs e < n_extra
+// (Wt = Wc0 transposed, [in][n_out]), zero elsewhere
+__global__ void fill_extra_cols_kernel(const float* __restrict__ Wt, int n_out, int n_extra, float* __restrict__ M, int ldm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 256 * 64) return;
+  int n = i >> 6, e = i & 63;
+  M[(size_t)n * ldm + 256 + e] = (n < n_out && e < n_extra) ? Wt[(size_t)e * n_out + n] : 0.f;
 }
 
 size_t tc_pack_bytes() {
@@ -1002,7 +1153,6 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   c.scales = a.take<float>(2 * 32);
   c.inv_scale = a.take<float>(32);
   float* w8row = a.take<float>(256);
-  float* W0x = a.take<float>(32 * 256);
   float* Wrgb = a.take<float>(3 * 256);
   float* b8feat = a.take<float>(256);      // b8[1:], 16-byte aligned copy (the epilogue loads float4)
   MP_REQUIRE(a.ok, "tc_pack: storage too small");
@@ -1017,7 +1167,6 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   P.inj_col = kHidden - E;
   P.w8row = w8row;
   P.b8 = f.imp_b[8];
-  P.W0x = W0x;
   P.Wrgb = Wrgb;
   P.n_extra = f.ren_extra;
   copy_strided_kernel<<<1, 256, 0, st>>>(f.imp_W[8], 1, 256, w8row);     // W8[0,:]
@@ -1065,7 +1214,9 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
   // The feature layer L8 and the colour layer 0 have no non-linearity in between (networks.py:199-207 -> :281,:305):
   //   C0_pre = Wc0[:, feat] (W8[1:] h7 + b8[1:]) + Wc0[:, extra] extra + b0  =  M h7 + (Wc0f b8f + b0) + ...
   // so the fused chains run ONE layer with M = Wc0[:, feat] . W8[1:, :] instead of two.
-  float* Mfold = a.take<float>(256 * 256);
+  // the colour layer 0 the chains run: [ M | extra-input columns | 0 ]  (256 x 320, K-blocks 0..3 | 4)
+  constexpr int kLdM = 320;
+  float* Mfold = a.take<float>(256 * kLdM);
   f.ren_cb = a.take<float>(264);
   f.ren_b0_fold = a.take<float>(264);
   MP_REQUIRE(a.ok, "tc_pack: storage too small");
@@ -1074,22 +1225,23 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
     const int coff = f.ren_mode == 0 ? 14 : f.ren_extra + 32;
     const int o0 = f.ren_out[0];
     fold_mm_kernel<<<dim3(256 / 16, div_up(o0, 16)), dim3(16, 16), 0, st>>>(f.ren_W[0], in0, coff, f.imp_W[8] + 256, 256,
-                                                                          f.imp_b[8] + 1, o0, Mfold, f.ren_cb);
+                                                                          f.imp_b[8] + 1, o0, Mfold, kLdM, f.ren_cb);
+    g_launches++;
+    MP_REQUIRE(f.ren_extra <= 64, "tc_pack: more than 64 extra colour inputs");
+    fill_extra_cols_kernel<<<64, 256, 0, st>>>(f.ren_Wt[0], o0, f.ren_extra, Mfold, kLdM);
     g_launches++;
   }
   if (bg_chain) {
     // background: folded colour layer 0 (view embedding + h7 -> 128, ReLU) and the rgb head (multiply.py:531)
     const int o0 = f.ren_out[0];
-    pack_layer(c, P.step[s], Mfold, 256, 0, 0, 0, o0, 256, 4, 256 * 256);
-    P.step[s].nk = 4;
+    pack_layer(c, P.step[s], Mfold, kLdM, 0, 0, 0, o0, kLdM, 5, 256 * kLdM);
+    P.step[s].nk = 5;
     P.step[s].epi = EPI_RELU;
     P.step[s].flags = F_EXTRA_IN | F_RGB_OUT;
     P.step[s].sig = -1;
     P.step[s].bias = f.ren_b0_fold;
     P.step[s].ncols = o0;
     ++s;
-    pad_rows_kernel<<<div_up(f.ren_extra * 256, 256), 256, 0, st>>>(f.ren_Wt[0], o0, f.ren_extra, o0, W0x);
-    g_launches++;
     pad_rows_kernel<<<div_up(3 * 256, 256), 256, 0, st>>>(f.ren_W[1], o0, 3, o0, Wrgb);
     g_launches++;
     P.brgb = f.ren_b[1];
@@ -1126,10 +1278,10 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
     // ---- colour net: folded layer 0, then layers 1..3 ----
     for (int l = 0; l < 4; ++l) {
       if (l == 0)
-        pack_layer(c, P.step[s], Mfold, 256, 0, 0, 0, 256, 256, 4, 256 * 256);
+        pack_layer(c, P.step[s], Mfold, kLdM, 0, 0, 0, 256, kLdM, 5, 256 * kLdM);
       else
         pack_layer(c, P.step[s], f.ren_W[l], 256, 0, 0, 0, 256, 256, 4, 256 * 256);
-      P.step[s].nk = 4;
+      P.step[s].nk = (l == 0) ? 5 : 4;
       P.step[s].epi = EPI_RELU;
       P.step[s].flags = ((l == 0) ? F_EXTRA_IN : 0) | ((l == 3) ? F_RGB_OUT : 0);
       P.step[s].sig = -1;
@@ -1137,8 +1289,7 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
       P.step[s].ncols = 256;
       ++s;
     }
-    // extra-input columns of colour layer 0 (x_c, n), transposed [6][256]; rgb head [3][256]
-    MP_CHECK_CUDA(cudaMemcpyAsync(W0x, f.ren_Wt[0], (size_t)6 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // rgb head [3][256]
     MP_CHECK_CUDA(cudaMemcpyAsync(Wrgb, f.ren_W[4], (size_t)3 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     P.brgb = f.ren_b[4];
     P.nsteps = s;
@@ -1152,6 +1303,13 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+int tc_trace_read(unsigned long long* out, int n) {
+  if (n > 4096) n = 4096;
+  MP_CHECK_CUDA(cudaDeviceSynchronize());
+  MP_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_trace, (size_t)n * sizeof(unsigned long long)));
+  return 0;
+}
+
 size_t tc_workspace_bytes(int N) { return (size_t)sm_count() * kScratchPerCta + 4096; }
 
 // optional per-launch timing of the tcgen05 kernel (bench.py roofline): CUDA events on the
@@ -1220,6 +1378,14 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
              ws_bytes, (size_t)grid * kScratchPerCta);
   io.scratch = (char*)ws;
   io.scratch_per_cta = kScratchPerCta;
+  {
+    static int knobs = -1;
+    if (knobs < 0) {
+      const char* ek = getenv("MP_TC_KNOBS");
+      knobs = ek ? atoi(ek) : 0;
+    }
+    io.knobs = knobs;
+  }
   static bool attr_set = false;
   static int nw = 16;
   static int pipe = 1; // K-block-granular hand-over with two accumulators (MP_TC_PIPE=0: whole-layer hand-over)

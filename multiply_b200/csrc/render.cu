@@ -17,6 +17,7 @@ int tc_shade_list(const Field& f, const float* xc_list, const int* slot_list, co
 int tc_bg(const Field& f, const float* pts, const float* dirs, int N, float* sdf, float* rgb, void* ws,
           size_t ws_bytes, cudaStream_t st);
 size_t tc_workspace_bytes(int N);
+int tc_trace_read(unsigned long long* out, int n);
 int prof_enable(int on);
 int prof_read(double* ms, long long* launches, double* points, int reset);
 
@@ -158,6 +159,11 @@ int mp_set_engine(int engine) {
 int mp_get_engine(void) { return mp::g_engine; }
 
 int mp_profile_enable(int on) { return mp::prof_enable(on); }
+int mp_tc_trace_read(unsigned long long* out, int n) {
+  MP_REQUIRE(out && n > 0, "mp_tc_trace_read: null argument");
+  return mp::tc_trace_read(out, n);
+}
+
 int mp_profile_read(double* ms_host, long long* launches_host, double* points_host, int reset) {
   MP_REQUIRE(ms_host && launches_host && points_host, "mp_profile_read: null argument");
   return mp::prof_read(ms_host, launches_host, points_host, reset);
