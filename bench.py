@@ -296,7 +296,9 @@ def main():
             "sampler_trips": trips, "engine": args.engine,
         }
         # issued tensor FLOPs: every step of every tile is 3 MMAs of 128x256x(64*nk)
-        steps_nk = {0: 29, 1: 33, 2: 77, 3: 34}   # 64-wide K chunks per tile of each program (mlp_tc.cu:tc_pack)
+        # 64-wide K chunks per tile of each program (mlp_tc.cu:tc_pack); the shade and background chains carry one
+        # extra K-block for the colour net's extra inputs
+        steps_nk = {0: 29, 1: 33, 2: 78, 3: 35}
         issued = 0.0
         for k in range(4):
             tiles = pp[k] / 128.0

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+for g in 0 74 111; do
+MP_TC_GRID=$g timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('GRID $g value',round(d['value']),'ms',round(d['ms_per_step'],3),'kernel_ms',round(d['roofline']['kernel_ms_per_step'],3))"
+done
