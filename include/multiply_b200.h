@@ -93,6 +93,9 @@ int mp_field_set_cond(mp_net_t* f, const float* cond /*[cond_dim]*/, void* strea
 /* engine selection: 0 = fp32 SIMT (validation engine), 1 = tcgen05 split-fp16 tensor-core engine */
 int mp_set_engine(int engine);
 int mp_get_engine(void);
+/* mp_render_rays schedule: 1 (default) = persons and background on their own streams, joined before the compositor;
+ * 0 = everything on the caller's stream (used for per-kernel timing).  Environment override: MP_RENDER_STREAMS. */
+int mp_set_streams(int on);
 
 /* Per-launch timing of the tcgen05 MLP kernel (CUDA events on the launching stream), by program kind:
  * [0] sdf-only, [1] forward (sdf + features), [2] full shade, [3] background.  mp_profile_read synchronises

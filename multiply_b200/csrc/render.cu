@@ -99,6 +99,29 @@ __global__ void iota_kernel(int* p, int n, int* count) {
 // beta < 0.23.  (The SDF clamp itself, multiply.py:142-143, is always exact.)
 static bool prune_is_exact(float beta) { return (4.0f / beta) > 18.0f; }
 
+// The persons of a scene and the background are independent until the compositor (multiply.py:266-410 is a Python
+// loop over persons; :514-539 only needs the rays).  Each branch runs on its own stream so that the small
+// latency-bound kernels of one (deformer, sampler trips) fill the SMs under the persistent MLP kernel of another,
+// which issues on a third of the cycles.  mp_set_streams(0) restores the single-stream schedule.
+struct BranchStreams {
+  bool ready = false;
+  cudaStream_t s[MP_MAX_PERSONS + 1];
+  cudaEvent_t fork, join[MP_MAX_PERSONS + 1];
+};
+static BranchStreams g_bs;
+static int g_streams_on = -1;
+
+static int branch_streams_init() {
+  if (g_bs.ready) return 0;
+  for (int i = 0; i <= MP_MAX_PERSONS; ++i) {
+    MP_CHECK_CUDA(cudaStreamCreateWithFlags(&g_bs.s[i], cudaStreamNonBlocking));
+    MP_CHECK_CUDA(cudaEventCreateWithFlags(&g_bs.join[i], cudaEventDisableTiming));
+  }
+  MP_CHECK_CUDA(cudaEventCreateWithFlags(&g_bs.fork, cudaEventDisableTiming));
+  g_bs.ready = true;
+  return 0;
+}
+
 struct PersonBufs {
   float *dirs, *cam, *z, *sdf, *rgb, *nrm, *xc_list, *jinv;
   int *slot_list, *count, *row_of_ray;
@@ -108,7 +131,8 @@ struct PersonBufs {
 struct RenderWs {
   float *dirs, *cam, *fg, *nrm, *acc, *accp, *bgT, *bg;
   PersonBufs pb[MP_MAX_PERSONS];
-  void* sub;
+  // scratch of the sampler / MLP engine: one per concurrently running branch (persons, background)
+  void* sub[MP_MAX_PERSONS + 1];
   size_t sub_bytes;
 };
 
@@ -143,7 +167,7 @@ static bool render_carve(Arena& a, const mp_scene_t& sc, int R, RenderWs& w) {
     sub = max(sub, engine_ws_bytes(Rp * n));
   }
   w.sub_bytes = sub;
-  w.sub = a.take<char>(sub);
+  for (int i = 0; i <= sc.P; ++i) w.sub[i] = a.take<char>(sub);     // [P] = background branch
   return a.ok;
 }
 
@@ -159,6 +183,11 @@ int mp_set_engine(int engine) {
 int mp_get_engine(void) { return mp::g_engine; }
 
 int mp_profile_enable(int on) { return mp::prof_enable(on); }
+int mp_set_streams(int on) {
+  mp::g_streams_on = on ? 1 : 0;
+  return 0;
+}
+
 int mp_tc_trace_read(unsigned long long* out, int n) {
   MP_REQUIRE(out && n > 0, "mp_tc_trace_read: null argument");
   return mp::tc_trace_read(out, n);
@@ -243,9 +272,31 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
   MP_REQUIRE(render_carve(a, *scene, R, w), "mp_render_rays: workspace too small (%zu needed, %zu given)", a.off,
              workspace_bytes);
   MP_TRY(mp_camera_rays(uv, pose, intrinsics, R, w.dirs, w.cam, stream));     // multiply.py:223-227
+  if (g_streams_on < 0) {
+    const char* e = getenv("MP_RENDER_STREAMS");
+    g_streams_on = e ? (atoi(e) != 0) : 1;
+  }
+  const bool fork = g_streams_on == 1;
+  const cudaStream_t caller = st;
+  if (fork) {
+    MP_TRY(branch_streams_init());
+    MP_CHECK_CUDA(cudaEventRecord(g_bs.fork, caller));
+  }
+  // background branch first: its MLP launch is the longest independent piece (multiply.py:514-541)
+  const float* bg = nullptr;
+  if (scene->bg_field) {
+    cudaStream_t sb = fork ? g_bs.s[scene->P] : caller;
+    if (fork) MP_CHECK_CUDA(cudaStreamWaitEvent(sb, g_bs.fork, 0));
+    MP_TRY(render_background(scene->bg_field->f, w.dirs, w.cam, R, c.scene_bounding_sphere, w.bg, w.sub[scene->P],
+                             w.sub_bytes, sb));
+    if (fork) MP_CHECK_CUDA(cudaEventRecord(g_bs.join[scene->P], sb));
+    bg = w.bg;
+  }
   CompositePersons cp;
   cp.P = scene->P;
   for (int p = 0; p < scene->P; ++p) {
+    st = fork ? g_bs.s[p] : caller;
+    if (fork) MP_CHECK_CUDA(cudaStreamWaitEvent(st, g_bs.fork, 0));
     MP_REQUIRE(scene->body[p] && scene->field[p] && scene->hit_index[p] && scene->hit_count[p] >= 1,
                "mp_render_rays: person %d incomplete", p);
     const Body& body = scene->body[p]->b;
@@ -256,7 +307,7 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
     gather_rays_kernel<<<div_up(Rp, 256), 256, 0, st>>>(w.dirs, w.cam, scene->hit_index[p], Rp, b.dirs, b.cam);
     MP_LAUNCH_CHECK();
     // ray_sampler.get_z_vals (multiply.py:285-289)
-    MP_TRY(sample_rays(c, body, field, b.dirs, b.cam, Rp, b.z, nullptr, out->trips ? out->trips + p : nullptr, w.sub,
+    MP_TRY(sample_rays(c, body, field, b.dirs, b.cam, Rp, b.z, nullptr, out->trips ? out->trips + p : nullptr, w.sub[p],
                        w.sub_bytes, st));
     // main pass (multiply.py:295-308, 403-404): deform, SDF, normals, colour
     MP_CHECK_CUDA(cudaMemsetAsync(b.count, 0, sizeof(int), st));
@@ -266,7 +317,7 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
                               b.slot_list, b.count, b.outl, nullptr, st));
     MP_TRY(launch_forward_jac(body, b.xc_list, Rp * n, b.count, nullptr, b.jinv, 12, st));
     MP_TRY(field_shade_list(field, b.xc_list, b.slot_list, b.count, Rp * n, b.jinv, b.sdf, b.rgb, b.nrm, nullptr,
-                            nullptr, w.sub, w.sub_bytes, st));
+                            nullptr, w.sub[p], w.sub_bytes, st));
     if (!prune) {
       force_outlier_sdf_kernel<<<div_up(Rp * n, 256), 256, 0, st>>>(b.outl, Rp * n, b.sdf);
       MP_LAUNCH_CHECK();
@@ -286,18 +337,18 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
     MP_TRY(tap(out->sdf[p], b.sdf, (size_t)Rp * n));
     MP_TRY(tap(out->rgb[p], b.rgb, (size_t)Rp * n * 3));
     MP_TRY(tap(out->normals[p], b.nrm, (size_t)Rp * n * 3));
+    if (fork) MP_CHECK_CUDA(cudaEventRecord(g_bs.join[p], st));
+  }
+  st = caller;
+  if (fork) {
+    for (int p = 0; p < scene->P; ++p) MP_CHECK_CUDA(cudaStreamWaitEvent(caller, g_bs.join[p], 0));
+    if (scene->bg_field) MP_CHECK_CUDA(cudaStreamWaitEvent(caller, g_bs.join[scene->P], 0));
   }
   float* normal = out->normal_values ? out->normal_values : w.nrm;
   float* acc = out->acc_map ? out->acc_map : w.acc;
   float* accp = out->acc_person_list ? out->acc_person_list : w.accp;
   float* bgT = out->bg_T ? out->bg_T : w.bgT;
   MP_TRY(launch_composite(cp, R, n, beta, w.fg, normal, acc, accp, bgT, st));     // multiply.py:427-480
-  const float* bg = nullptr;
-  if (scene->bg_field) {                                                          // multiply.py:514-541
-    MP_TRY(render_background(scene->bg_field->f, w.dirs, w.cam, R, c.scene_bounding_sphere, w.bg, w.sub, w.sub_bytes,
-                             st));
-    bg = w.bg;
-  }
   MP_REQUIRE(out->rgb_values, "mp_render_rays: rgb_values output is required");
   MP_TRY(launch_final_compose(w.fg, bgT, bg, R, out->rgb_values, out->fg_rgb_values, st));   // :544-545, :590
   return 0;

@@ -239,6 +239,30 @@ def test_more_persons_and_samples(P, Sn, R):
         assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < tol, k
 
 
+def test_branch_streams_match_single_stream():
+    """mp_render_rays runs persons and background on their own streams (joined before the compositor); the result
+    must be bit-identical to the single-stream schedule, call after call (workspace reuse across calls)."""
+    from multiply_b200 import engine, _lib as L
+    engine.set_engine("tc")
+    sc = S.make_scene(P=3, S=64, seed=7)
+    inp = S.make_rays(sc, 300, seed=3, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    r = engine.Renderer(sc)
+    lib = L.lib()
+    try:
+        L.check(lib.mp_set_streams(0), "mp_set_streams")
+        ref = {k: v.clone() for k, v in r.render(inp, hits).items()}
+        torch.cuda.synchronize()
+        L.check(lib.mp_set_streams(1), "mp_set_streams")
+        for _ in range(3):
+            o = r.render(inp, hits)
+            torch.cuda.synchronize()
+            for k in ("rgb_values", "fg_rgb_values", "normal_values", "acc_map", "acc_person_list"):
+                assert torch.equal(o[k], ref[k]), k
+    finally:
+        lib.mp_set_streams(1)
+
+
 def test_edge_cases_single_ray_and_no_hits():
     """R = 1, and a batch in which no ray hits any box (every hit list empty -> ray 0, multiply.py:262-263):
     the outputs equal the oracle's and untouched rays are pure background (acc 0, bg_T 1)."""
