@@ -235,6 +235,12 @@ int mp_composite(const mp_person_samples_t* persons_host, int P, int R, int n, f
                  float* fg_rgb, float* normal, float* acc, float* acc_person, float* bg_T,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* rgb_values = fg_rgb + bg_T * bg_rgb (bg_rgb NULL -> white, multiply.py:540-545), fg_rgb_values = fg_rgb + bg_T * 1
+ * (multiply.py:590); fg_rgb_values may be NULL.  The last stage of Multiply.forward, exported for callers that composite
+ * ray blocks themselves (person-sharded rendering, multiply_b200/parallel.py). */
+int mp_final_compose(const float* fg_rgb /*[R,3]*/, const float* bg_T /*[R]*/, const float* bg_rgb /*[R,3] or NULL*/, int R,
+                     float* rgb_values /*[R,3]*/, float* fg_rgb_values /*[R,3] or NULL*/, void* stream);
+
 /* background: inverse-sphere samples -> depth2pts_outside (multiply.py:698-726) -> bg nets -> bg_volume_rendering */
 size_t mp_background_workspace_bytes(int R);
 int mp_background(mp_net_t* bg_field, const float* ray_dirs, const float* cam_loc, int R, float bound_r,

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mp_sdf_with_deformer": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mp_composite_workspace_bytes": (_SZ, [_I, _I]),
     "mp_composite": (_I, [C.POINTER(PersonSamples), _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mp_final_compose": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_background_workspace_bytes": (_SZ, [_I]),
     "mp_background": (_I, [_VP, _VP, _VP, _I, _F, _VP, _VP, _SZ, _VP]),
     "mp_render_workspace_bytes": (_SZ, [C.POINTER(Scene), _I]),

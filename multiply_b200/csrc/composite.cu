@@ -226,4 +226,11 @@ int mp_composite(const mp_person_samples_t* persons, int P, int R, int n, float 
   }
   return mp::launch_composite(cp, R, n, beta, fg_rgb, normal, acc, acc_person, bg_T, st);
 }
+
+int mp_final_compose(const float* fg_rgb, const float* bg_T, const float* bg_rgb, int R, float* rgb_values,
+                     float* fg_rgb_values, void* stream) {
+  MP_REQUIRE(fg_rgb && bg_T && rgb_values, "mp_final_compose: null argument");
+  if (R <= 0) return 0;
+  return mp::launch_final_compose(fg_rgb, bg_T, bg_rgb, R, rgb_values, fg_rgb_values, (cudaStream_t)stream);
+}
 }

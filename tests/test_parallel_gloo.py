@@ -62,3 +62,54 @@ def test_two_rank_gather_equals_unsharded():
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert sorted((lo, hi) for _, _, lo, hi in res) == [(0, 501), (501, 1001)]
+
+
+# ---- person-sharded exchange: plan + all-to-all by ray block, world_size 2 and 3 ----
+def test_exchange_plan_partitions_every_hit_list():
+    g = torch.Generator().manual_seed(1)
+    total = 1000
+    hits = [torch.sort(torch.randperm(total, generator=g)[:k])[0] for k in (1, 37, 999, 1000)]
+    hits.append(torch.zeros(1, dtype=torch.int64))       # the ray-0 substitute of an empty list
+    assert [h.tolist() for h in parallel.normalize_hits([[], [3, 5]])] == [[0], [3, 5]]
+    for world in (1, 2, 3, 8):
+        plan = parallel.exchange_plan(hits, total, world)
+        for h, pl in zip(hits, plan):
+            assert pl[0][0] == 0 and pl[-1][1] == h.numel()
+            for b, (lo, hi) in enumerate(pl):
+                blo, bhi = parallel.shard_bounds(total, b, world)
+                assert all(blo <= int(r) < bhi for r in h[lo:hi])
+                if b + 1 < world:
+                    assert hi == pl[b + 1][0]
+
+
+def _xchg_worker(rank, world, port, total, P, width, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    hits = [torch.sort(torch.randperm(total, generator=g)[: 50 + 40 * p])[0] for p in range(P)]
+    full = [torch.rand(h.numel(), width, generator=g) for h in hits]        # what the owners would compute
+    plan = parallel.exchange_plan(hits, total, world)
+    rows = {p: full[p] for p in range(P) if parallel.person_owner(p, world) == rank}
+    got = parallel.exchange_person_rows(rows, plan, width, rank, world, torch.device("cpu"))
+    lo, hi = parallel.shard_bounds(total, rank, world)
+    ok = True
+    for p in range(P):
+        sel = (hits[p] >= lo) & (hits[p] < hi)
+        ok = ok and torch.equal(got[p], full[p][sel])
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_person_rows_exchange_gloo():
+    for world, P in ((2, 2), (3, 5)):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_xchg_worker, args=(r, world, port, 777, P, 9, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+        assert all(ok for _, ok in res), res
