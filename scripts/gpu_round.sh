@@ -1,8 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
-timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3
-timeout 600 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_tc.json
-MP_TC_EPI_WARPS=8 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_tc_w8.json
-MP_ENGINE=simt timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_simt.json
+# what the driver runs at round end: gpu tests, smoke, the default bench line and the reference arm
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
+timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_default.json
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/bench_reference.json
