@@ -80,7 +80,7 @@ struct TcIO {
   float* nrm_out;        // [slots,3]
   float* grad_out;       // [cap,3] dense or nullptr
   float* feat_out;       // [cap,256] dense or nullptr
-  int knobs;             // experiment switches (MP_TC_KNOBS bit mask), 0 in production
+  int knobs;             // diagnostics (MP_TC_KNOBS bit mask): bit 1 = record the cycle stamps of mp_tc_trace_read
   char* scratch;         // per-CTA scratch
   size_t scratch_per_cta;
 };
@@ -124,22 +124,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
-}
-// bounded variant for the timing-experiment lanes (may lag more than one phase behind: never spin forever)
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity, int max_tries) {
-  for (int i = 0; i < max_tries; ++i) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -417,38 +401,11 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             int r = it % kRing;
             uint32_t ph = (it / kRing) & 1;
             mbar_wait(&empty[r], ph ^ 1);
-            const bool twice = io.knobs & 4;   // timing experiment: fetch every slot twice (same result, 2x weight traffic)
-            mbar_expect_tx(&full[r], twice ? 2 * kSlotBytes : kSlotBytes);
+            mbar_expect_tx(&full[r], kSlotBytes);
             bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)j * kSlotBytes, kSlotBytes, &full[r]);
-            if (twice) bulk_g2s(ring + (size_t)r * kSlotBytes, src + (size_t)j * kSlotBytes, kSlotBytes, &full[r]);
           }
         }
       }
-    }
-    else if (io.knobs & 8) {
-      // timing experiment: lanes 1..31 shadow the loader and pull one more slot's worth of (other) weights through L2
-      // per ring refill with plain L2 loads (results unchanged, ~2x weight traffic, no request merging)
-      uint32_t it = 0;
-      unsigned acc = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int s = 0; s < P.nsteps; ++s) {
-          const int nslot = 2 * P.step[s].nk;
-          for (int j = 0; j < nslot; ++j, ++it) {
-            int r = it % kRing;
-            uint32_t ph = (it / kRing) & 1;
-            mbar_wait_bounded(&empty[r], ph ^ 1, 64);
-            const int other = (P.step[s].slot_off + j + P.slots_per_tile / 2) % P.slots_per_tile;
-            const uint4* q = (const uint4*)((const char*)P.blob + (size_t)other * kSlotBytes) + (lane - 1) * 66;
-#pragma unroll 11
-            for (int k = 0; k < 66; ++k) {
-              uint4 w;
-              asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(q + k));
-              acc ^= w.x ^ w.y ^ w.z ^ w.w;
-            }
-          }
-        }
-      }
-      if (acc == 0x12345679u) g_trace[4095] = acc;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
