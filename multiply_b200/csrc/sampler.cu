@@ -424,22 +424,32 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
   int wpc_b = clamp_wpc((size_t)(200 * 1024) / per_warp_beta);
   int wpc_r = clamp_wpc((size_t)(200 * 1024) / per_warp_res);
   MP_REQUIRE(per_warp_res <= 220 * 1024, "sampler: N_samples_eval too large for shared memory");
+  // every trip's launch asks for warps * per-warp bytes <= 200 KB (or one warp of the longest list)
+  const size_t smem_cap = (size_t)200 * 1024;
   MP_CHECK_CUDA(cudaFuncSetAttribute(sampler_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(wpc_b * per_warp_beta)));
+                                     (int)max(smem_cap, (size_t)wpc_b * per_warp_beta)));
   MP_CHECK_CUDA(cudaFuncSetAttribute(sampler_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(wpc_r * per_warp_res)));
+                                     (int)max(smem_cap, (size_t)wpc_r * per_warp_res)));
+  const int wpc_for_trip = 8;      // warps (= rays) per block: small blocks spread a 4096-ray batch over all SMs
   for (int t = 0; t < c.max_total_iters; ++t) {
     const int M = (t + 1) * E;
     // SDF of the E new samples of every ray (multiply.py:137-151 under no_grad, ray_sampler.py:82-88)
     MP_TRY(launch_deform_rays(body, dirs, cam, zc, zcap, t == 0 ? nullptr : w.pos_new, E, E, R, /*prune=*/1, sc,
                               zcap, w.xc_list, w.slot_list, &w.st->count[t], nullptr, &w.st->active[t], st));
     MP_TRY(field_sdf_list(field, w.xc_list, w.slot_list, &w.st->count[t], R * E, sc, w.mlp_ws, w.mlp_ws_bytes, st));
-    sampler_beta_kernel<<<div_up(R, wpc_b), wpc_b * 32, wpc_b * per_warp_beta, st>>>(
-        zc, sc, zcap, M, R, beta0, c.eps, c.beta_iters, t, w.beta, w.st, mmax);
+    // shared memory per ray sized for THIS trip's list (M = (t+1) E entries; the final-set staging needs X + 2):
+    // trip 0 -- usually the only active one -- then keeps every ray of the batch resident at once instead of
+    // 13 warps per SM sized for the longest possible list
+    const int stride = max(M, X + 2);
+    const size_t pw_b = (size_t)3 * stride * sizeof(float), pw_r = (size_t)(4 * stride + E) * sizeof(float);
+    const int wb = min(wpc_for_trip, clamp_wpc((size_t)(200 * 1024) / pw_b));
+    const int wr = min(wpc_for_trip, clamp_wpc((size_t)(200 * 1024) / pw_r));
+    sampler_beta_kernel<<<div_up(R, wb), wb * 32, wb * pw_b, st>>>(
+        zc, sc, zcap, M, R, beta0, c.eps, c.beta_iters, t, w.beta, w.st, stride);
     MP_LAUNCH_CHECK();
-    sampler_resample_kernel<<<div_up(R, wpc_r), wpc_r * 32, wpc_r * per_warp_res, st>>>(
+    sampler_resample_kernel<<<div_up(R, wr), wr * 32, wr * pw_r, st>>>(
         zc, sc, zcap, M, R, E, S, X, c.max_total_iters, c.add_tiny, c.near, t, w.beta, w.far, w.tab, zn, sn,
-        w.pos_new, z_final, w.st, mmax);
+        w.pos_new, z_final, w.st, stride);
     MP_LAUNCH_CHECK();
     float* tz = zc; zc = zn; zn = tz;
     float* ts = sc; sc = sn; sn = ts;
