@@ -3,7 +3,7 @@
 //   reference: /root/reference/code/lib/model/networks.py:126-208 (ImplicitNet.forward),
 //              :263-312 (RenderingNet.forward), lib/model/multiply.py:620-661 (forward_gradient)
 //
-// Design (DESIGN.md §kernels):
+// Design (DESIGN.md §3.1):
 //   * one persistent CTA per SM; a tile is 128 sample points (MMA M = 128, cta_group::1).
 //   * every layer is D[128 x 256] (fp32, 256 TMEM columns) = A[128 x K] . W^T, K in chunks of 64.
 //     A (the activations) lives in shared memory as fp16 hi + fp16 lo (K-major, 128B swizzle);
@@ -13,9 +13,13 @@
 //     fp32 accumulate) — 22 significand bits per operand, which is what keeps RGB/SDF within the
 //     1e-4 gate that a single bf16/fp16 pass misses by two orders of magnitude.
 //   * warp roles: warp 0 = weight loader, warp 1 = MMA issuer (one elected lane),
-//     warps 2..9 = epilogue (TMEM -> registers -> activation -> fp16 hi/lo -> shared memory).
+//     warps 2..17 = epilogue (TMEM -> registers -> activation -> fp16 hi/lo -> shared memory):
+//     TMEM lane quadrant x column part; a part owns 16 columns of each 64-wide K-block of the next
+//     operand and hands them over K-block by K-block, so the next layer's MMAs start after a quarter
+//     of the epilogue, into the other of two accumulators (512 TMEM columns in all).
 //   * the whole per-sample chain runs inside the tile: embed, L0..L7 (+ sigma' stash), SDF dot,
-//     L8 features, the reverse sweep B7..B0 (d sdf / d x_c), normals, colour layers, RGB.
+//     the reverse sweep B7..B0 (d sdf / d x_c), normals, colour layers (the feature layer L8 folded
+//     into colour layer 0, its extra inputs as a fifth K-block), RGB.
 #include "common.cuh"
 #include <vector>
 #include <stdlib.h>
