@@ -83,6 +83,22 @@ class Multiply(nn.Module):
         d["cond"] = cond if cond is not None else torch.zeros(1, 69)
         return d
 
+    # ---- operator surface the sampler / callers use (multiply.py:137-151) --------------------------
+    def sdf_func_with_smpl_deformer(self, x, cond, smpl_tfs, smpl_verts, person_id):
+        """multiply.py:137-151: canonicalise x against person ``person_id``'s posed SMPL (nearest vertex, inverse
+        LBS), evaluate the SDF network there, set outliers (> 0.1 from the body, deformer.py:49) to sdf = 4 in eval
+        mode.  Returns (sdf [N,1], x_c [N,3], feature [N,256])."""
+        x_c, outlier_mask = self.deformer_list[person_id].forward(x, smpl_tfs, return_weights=False, inverse=True,
+                                                                  smpl_verts=smpl_verts)
+        output = self.foreground_implicit_network_list[person_id](x_c, cond, person_id=person_id)[0]
+        sdf = output[:, 0:1].clone()
+        if not self.training:
+            sdf[outlier_mask] = 4.0                                         # multiply.py:142-143
+        if not self.with_bkgd and self.sdf_bounding_sphere > 0.0:
+            raise NotImplementedError("with_bkgd=False (sphere clamp, multiply.py:145-148) is not on the shipped path")
+        feature = output[:, 1:]
+        return sdf, x_c, feature
+
     # ---- Multiply.forward, eval branch -------------------------------------------------------
     def forward(self, input, id=-1, cond_zero_shit=False, canonical_pose=False):
         if self.training:
