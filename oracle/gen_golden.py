@@ -245,23 +245,42 @@ def main():
     save("smpl_lbs", betas=betas, pose=pose, verts=verts[0], A=A[0])
 
     # ---- sampler + full forward -----------------------------------------------------
-    for name, Sn, R, region in (("forward_S64_R48", 64, 48, "boxes"), ("forward_S16_R96", 16, 96, "image")):
-        sc = S.make_scene(P=2, S=Sn, seed=42)
-        mm = build_ref_model(ref, sc)
-        inputs = S.make_rays(sc, R, seed=1234, region=region)
-        hits = S.make_hit_lists(sc, inputs)
-        o = ref_forward(ref, mm, sc, inputs, hits)
-        flat = {k: v for k, v in o.items() if isinstance(v, torch.Tensor)}
-        for p in range(2):
-            flat[f"z_vals_{p}"] = o["z_vals"][p]
-            flat[f"sdf_{p}"] = o["sdf"][p]
-            flat[f"rgb_{p}"] = o["rgb"][p]
-            flat[f"normals_{p}"] = o["normals"][p]
-            flat[f"hits_{p}"] = hits[p]
-        flat["trips"] = np.array(o["trips"])
-        flat["uv"] = inputs["uv"]
-        save(name, **flat)
+    for case in FORWARD_CASES:
+        forward_case(ref, *case)
+
+
+# (name, persons, N_samples, rays, ray region, scene seed)
+FORWARD_CASES = (("forward_S64_R48", 2, 64, 48, "boxes", 42), ("forward_S16_R96", 2, 16, 96, "image", 42),
+                 ("forward_P3_S32_R40", 3, 32, 40, "boxes", 7))
+
+
+def forward_case(ref, name, P, Sn, R, region, seed):
+    """The reference's own sampler / deformer / networks / density objects driven through the eval branch of
+    Multiply.forward on a synthetic scene; everything the parity tests compare is stored."""
+    sc = S.make_scene(P=P, S=Sn, seed=seed)
+    mm = build_ref_model(ref, sc)
+    inputs = S.make_rays(sc, R, seed=1234, region=region)
+    hits = S.make_hit_lists(sc, inputs)
+    o = ref_forward(ref, mm, sc, inputs, hits)
+    flat = {k: v for k, v in o.items() if isinstance(v, torch.Tensor)}
+    for p in range(P):
+        flat[f"z_vals_{p}"] = o["z_vals"][p]
+        flat[f"sdf_{p}"] = o["sdf"][p]
+        flat[f"rgb_{p}"] = o["rgb"][p]
+        flat[f"normals_{p}"] = o["normals"][p]
+        flat[f"hits_{p}"] = hits[p]
+    flat["trips"] = np.array(o["trips"])
+    flat["uv"] = inputs["uv"]
+    save(name, **flat)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":      # regenerate single forward fixtures, e.g. --only forward_P3_S32_R40
+        torch.set_num_threads(8)
+        _ref = ref_shim.load()
+        for case in FORWARD_CASES:
+            if case[0] in sys.argv[2:]:
+                forward_case(_ref, *case)
+    else:
+        main()

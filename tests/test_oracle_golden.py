@@ -77,22 +77,23 @@ def test_deformer(golden_dir, scene64):
     assert np.abs(xd.numpy() - g["x_d"]).max() < 1e-6
 
 
-@pytest.mark.parametrize("name,Sn,R,region", [("forward_S64_R48", 64, 48, "boxes"),
-                                              ("forward_S16_R96", 16, 96, "image")])
-def test_forward(golden_dir, name, Sn, R, region):
+@pytest.mark.parametrize("name,P,Sn,R,region,seed", [("forward_S64_R48", 2, 64, 48, "boxes", 42),
+                                                     ("forward_S16_R96", 2, 16, 96, "image", 42),
+                                                     ("forward_P3_S32_R40", 3, 32, 40, "boxes", 7)])
+def test_forward(golden_dir, name, P, Sn, R, region, seed):
     g = _g(golden_dir, name)
-    sc = S.make_scene(P=2, S=Sn, seed=42)
+    sc = S.make_scene(P=P, S=Sn, seed=seed)
     inp = S.make_rays(sc, R, seed=1234, region=region)
     assert np.array_equal(inp["uv"].numpy(), g["uv"]), "synthetic input drifted from the golden's"
     hits = S.make_hit_lists(sc, inp)
-    for p in range(2):
+    for p in range(P):
         assert np.array_equal(hits[p].numpy(), g[f"hits_{p}"])
     st = {}
     o = port.multiply_forward(sc, inp, hits, stats=st, return_samples=True)
     assert list(st["trips"]) == list(g["trips"])
     for k in ("rgb_values", "fg_rgb_values", "normal_values", "acc_map", "acc_person_list"):
         assert np.abs(o[k].numpy() - g[k]).max() < 1e-5, k
-    for p in range(2):
+    for p in range(P):
         assert np.abs(o["_z_vals"][p].numpy() - g[f"z_vals_{p}"]).max() < 2e-4
         assert np.abs(o["_sdf"][p].numpy() - g[f"sdf_{p}"]).max() < 1e-4
 
