@@ -8,6 +8,13 @@ A "step" is one pass of the hot path (Multiply.forward, eval) over one batch of 
 BASELINE.json configs[1] = 2-person synthetic SMPL scene, 4096 rays x 128 samples (S/E/X = 128/256/64),
 1 x B200.  With N GPUs every rank renders its own 4096-ray block of a 4096*N-ray batch (weak scaling)
 and the rendered pixels are all-gathered over NCCL; `value` = all rays / max-over-ranks device time.
+
+`value`  : inputs (rays, hit lists, posed bodies) resident on the device, engine.Renderer.render.
+`e2e`    : the drop-in call — multiply_b200.model.multiply.Multiply.forward(input_dict) with the reference's input dict
+           in PINNED HOST memory: per step H2D of uv / pose / intrinsics / smpl_* / idx, SMPL server, posed-grid rebuild,
+           GPU ray/box culling, sampling, MLPs, compositing, D2H of rgb_values.
+Sub-records (same JSON line, `extras`): strong scaling of one 16 384-ray x 256-sample frame (configs[3]),
+person-sharded fields (configs[4]), a chunked 512x512 frame (configs[2]), dense SDF grid queries, precision modes.
 """
 import argparse
 import json
@@ -28,6 +35,8 @@ F_SDF, B_SDF, F_RGB, F_BG = 1084416, 918016, 532992, 1146880
 RAYS_PER_GPU = 4096
 S_SAMPLES = 128
 PERSONS = 2
+CPU_SAMPLE_RAYS = 512          # cpu_baseline leg of the GPU arm (timed once)
+REF_SAMPLE_RAYS = 128          # --impl reference: rays per step
 
 
 def measured_peaks():
@@ -74,16 +83,6 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(rank, world):
-    from multiply_b200 import scene as S
-    sc = S.make_scene(P=PERSONS, S=S_SAMPLES, seed=42)
-    inp = S.make_rays(sc, RAYS_PER_GPU * world, seed=1234, region="boxes")
-    lo, hi = rank * RAYS_PER_GPU, (rank + 1) * RAYS_PER_GPU
-    my = dict(uv=inp["uv"][:, lo:hi].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
-    hits = S.make_hit_lists(sc, my)
-    return sc, my, hits
-
-
 def config_dict(world):
     return {"workload": "configs[1]: 2-person synthetic SMPL scene, %d rays x %d samples per GPU "
                         "(S/E/X = 128/256/64, n = 193 main-pass samples), eval forward: sampler + deformer + "
@@ -91,9 +90,12 @@ def config_dict(world):
             "rays_per_gpu": RAYS_PER_GPU, "persons": PERSONS, "N_samples": S_SAMPLES,
             "global_rays": RAYS_PER_GPU * world,
             "precision": "fp16 hi/lo split x3 tcgen05 MMAs, fp32 accumulate (parity mode, RGB/SDF within 1e-4)",
-            "rays": "uniform in the persons' image-space bounding rectangle (hit lists by host slab test, "
-                    "excluded from timing on both arms as in BASELINE.md)",
+            "scene": "bodies from the device SMPL server (mp_smpl_forward) on a synthetic SMPL-shaped model, "
+                     "geometric-init networks (multiply_b200/scene.py:make_smpl_scene)",
+            "rays": "uniform in the persons' image-space bounding rectangle; `value`: hit lists resident (host slab test, "
+                    "as in BASELINE.md); `e2e`: culled on the GPU inside the timed region",
             "l2_flush": "256 MB device write between timed steps (outside the timed events)",
+            "cpu_sample_rays": {"cpu_baseline": CPU_SAMPLE_RAYS, "reference_arm_per_step": REF_SAMPLE_RAYS},
             "parallelism": "ray blocks sharded over %d GPU(s), one NCCL all_gather of pixels" % world}
 
 
@@ -113,6 +115,27 @@ def best_cpu_threads(fn):
     return best[0]
 
 
+def cpu_scene():
+    """The benchmark scene built WITHOUT this repo's kernels (reference arm): same networks, same SMPL inputs, the
+    bodies from the oracle's restatement of SMPLServer.forward (lib/model/smpl.py:50-95) instead of mp_smpl_forward —
+    the two agree to 5e-6 (tests/test_gpu_mirror.py::test_smpl_server_and_culling)."""
+    import math
+    from oracle import port
+    from multiply_b200 import scene as S
+    si = S.smpl_scene_inputs(PERSONS)
+    nets, rest = S.smpl_scene_networks(PERSONS, S_SAMPLES, 42)
+    persons = []
+    for p in range(PERSONS):
+        sm = S.make_smpl_model(300 + p, body_seed=100 + p)
+        tinv, vc = port.smpl_canonical_tfs_inv(sm, torch.zeros(10))
+        o = port.smpl_server_forward(sm, tinv, si["smpl_params"][0, p, :1], si["smpl_trans"][0, p], si["smpl_pose"][0, p],
+                                     torch.zeros(10))
+        persons.append(dict(verts_c=vc, weights=sm["lbs_weights"], verts_p=o["smpl_verts"], tfs=o["smpl_tfs"],
+                            smpl_pose=si["smpl_pose"][:, p].clone(), cond=si["smpl_pose"][:, p, 3:] / math.pi, scale=0.5,
+                            implicit=nets[p]["implicit"], render=nets[p]["render"]))
+    return dict(rest, persons=persons)
+
+
 def run_reference(args, rank, world):
     """The reference algorithm on the host CPU (oracle/port.py — pinned against the unmodified reference
     modules by tests/golden; the reference itself needs the absent SMPL pkl / trimesh / nerfacc / pytorch3d)."""
@@ -120,8 +143,8 @@ def run_reference(args, rank, world):
         return
     from oracle import port
     from multiply_b200 import scene as S
-    sc = S.make_scene(P=PERSONS, S=S_SAMPLES, seed=42)
-    n_sample = 48
+    sc = cpu_scene()
+    n_sample = REF_SAMPLE_RAYS
     inp = S.make_rays(sc, RAYS_PER_GPU, seed=1234, region="boxes")
     sub = dict(uv=inp["uv"][:, :n_sample].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
     hits = S.make_hit_lists(sc, sub)
@@ -148,6 +171,193 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+class Timer:
+    """K steps bracketed by barrier + synchronize, CUDA events per step on the current stream, L2 flush between
+    steps (outside the events), max over ranks."""
+
+    def __init__(self, dev, world, lib):
+        self.dev, self.world, self.lib = dev, world, lib
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run(self, fn, steps, warmup, profile=False):
+        import torch.distributed as dist
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        self.lib.mp_launch_count(1)
+        if profile:
+            self.lib.mp_profile_enable(1)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            self.flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
+            ev[i][0].record()
+            fn()
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = self.lib.mp_launch_count(0)
+        if profile:
+            self.lib.mp_profile_enable(0)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), int(launches)
+
+
+def linf(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+def extras_strong(timer, dev, rank, world, steps):
+    """BASELINE configs[3]: ONE 16 384-ray x 256-sample frame (2 persons, S/E/X = 256/512/128, n = 385) sharded N ways
+    over ray blocks (strong scaling): frame time, rays/s, and the gathered frame against the same frame rendered on
+    one GPU (bit-equal when the sampler's batch-global trip counts agree)."""
+    import torch.distributed as dist
+    from multiply_b200 import engine, parallel, scene as S
+    total = 16384
+    sc = S.make_scene(P=2, S=256, seed=42)
+    full = S.make_rays(sc, total, seed=77, region="boxes")
+    lo, hi = parallel.shard_bounds(total, rank, world)
+    mine = dict(uv=full["uv"][:, lo:hi].contiguous(), pose=full["pose"], intrinsics=full["intrinsics"])
+    hits = [h.to(dev) for h in S.make_hit_lists(sc, mine)]
+    d_in = {k: v.to(dev) for k, v in mine.items()}
+    r = engine.Renderer(sc, device=dev)
+    Rl = hi - lo
+    buf = parallel.PixelBuffer(Rl, 2, dev)
+    gathered = torch.empty(world, Rl * 12, device=dev) if world > 1 else None
+
+    def step():
+        r.render(d_in, hits, out=buf.views)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, buf.flat)
+
+    ms, _ = timer.run(step, steps, 3)
+    rec = {"config": "configs[3]: one %d-ray x 256-sample frame (2 persons, S/E/X = 256/512/128), %d rays per GPU" % (total, Rl),
+           "frame_ms": ms / steps, "rays_per_s": total * steps / (ms / 1000.0), "scaling": "strong"}
+    if world > 1:
+        frame = parallel.PixelBuffer.frame(gathered, world, Rl, 2)
+        if rank == 0:
+            fh = [h.to(dev) for h in S.make_hit_lists(sc, full)]
+            one = r.render({k: v.to(dev) for k, v in full.items()}, fh)
+            torch.cuda.synchronize()
+            rec["vs_single_gpu_frame"] = {"bit_equal": all(torch.equal(frame[k], one[k]) for k in parallel.PIXEL_KEYS),
+                                          "rgb_linf": linf(frame["rgb_values"], one["rgb_values"])}
+    return rec
+
+
+def extras_person_sharded(timer, dev, rank, world, steps):
+    """BASELINE configs[4]: 6 persons, 4096 rays x 128 samples, one canonical field per GPU (person p on rank p mod N),
+    all-to-all of sample rows by ray block, block compositing, pixel all-gather; against the fused single-GPU frame."""
+    import torch.distributed as dist
+    from multiply_b200 import engine, parallel, scene as S
+    P, R = 6, 4096
+    sc = S.make_scene(P=P, S=S_SAMPLES, seed=42)
+    inp = S.make_rays(sc, R, seed=1234, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    d_in = {k: v.to(dev) for k, v in inp.items()}
+    pr = parallel.PersonShardedRenderer(sc, device=dev)
+    out = {}
+
+    def step():
+        out["o"] = pr.render(d_in, hits)
+
+    ms, _ = timer.run(step, steps, 3)
+    n = sc["cfg"]["N_samples"] + sc["cfg"]["N_samples_extra"] + 1
+    # rows that leave their owner: every row of a person's hit list whose ray block is another rank's
+    plan = parallel.exchange_plan(parallel.normalize_hits(hits), R, world)
+    moved = sum(plan[p][b][1] - plan[p][b][0] for p in range(P) for b in range(world) if b != parallel.person_owner(p, world))
+    rec = {"config": "configs[4]: %d persons, %d rays x %d samples, field p on GPU p mod %d" % (P, R, S_SAMPLES, world),
+           "frame_ms": ms / steps, "rays_per_s": R * steps / (ms / 1000.0),
+           "all_to_all_bytes_per_frame": int(moved * (8 * n + 1) * 4), "persons_per_gpu": [len([p for p in range(P) if parallel.person_owner(p, world) == g]) for g in range(world)]}
+    if world > 1:
+        # time of the exchange alone (same rows, same plan)
+        rows = pr.person_rows(d_in, parallel.normalize_hits(hits))
+        pr._plan = plan
+
+        def xchg():
+            parallel.exchange_person_rows(rows, plan, pr.width, rank, world, dev, None)
+
+        xms, _ = timer.run(xchg, steps, 2)
+        rec["all_to_all_ms"] = xms / steps
+    if rank == 0:
+        one = engine.Renderer(sc, device=dev).render(d_in, [h.to(dev) for h in hits])
+        torch.cuda.synchronize()
+        rec["vs_single_gpu_frame"] = {"bit_equal": all(torch.equal(out["o"][k], one[k]) for k in parallel.PIXEL_KEYS),
+                                      "rgb_linf": linf(out["o"]["rgb_values"], one["rgb_values"])}
+    return rec
+
+
+def extras_full_frame(dev, rank, world):
+    """BASELINE configs[2]: 3 persons, 512 x 512 pixels, 256 samples/ray (S/E/X = 256/512/128), chunked in 16 384-ray
+    pieces through the drop-in Multiply.forward (idr_utils.split_input / merge_output, multiply_model.py:1235-1270);
+    with N GPUs the chunks are dealt round-robin.  One warm-up chunk, then the whole frame is timed once."""
+    import torch.distributed as dist
+    from multiply_b200 import scene as S
+    from multiply_b200.utils import idr_utils
+    res, chunk = 512, 16384
+    sc, model, smpl_in = S.make_smpl_scene(P=3, S=256, seed=42, device=dev)
+    frame = S.grid_rays(res=res)
+    inputs = {k: v.to(dev) for k, v in dict(frame, **smpl_in).items()}
+    chunks = idr_utils.split_input(inputs, res * res, n_pixels=chunk)
+    mine = chunks[rank::world]
+    with torch.no_grad():
+        model(mine[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res_list = [model(c) for c in mine]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    merged = idr_utils.merge_output(res_list, len(mine) * chunk, 1)
+    model._renderer.check_status()
+    return {"config": "configs[2]: 3 persons, %dx%d frame, 256 samples/ray, %d-ray chunks (%d chunks, %d per GPU)"
+                      % (res, res, chunk, len(chunks), len(mine)),
+            "frame_ms": float(ms.item()), "rays_per_s": res * res / (float(ms.item()) / 1000.0),
+            "rgb_mean": float(merged["rgb_values"].mean()), "acc_mean": float(merged["acc_map"].mean())}
+
+
+def extras_sdf_grid(dev):
+    """f3: canonical SDF on the dense 257^3 lattice of generate_mesh (lib/utils/mesh.py:78-105) in one mp_sdf_grid call,
+    and the same number of points in 10 000-point query_oc batches (point_batch of the reference's mesh refresh)."""
+    from multiply_b200 import engine, scene as S
+    sc = S.make_scene(P=1, S=16, seed=42)
+    p0 = sc["persons"][0]
+    f = engine.Field(p0["implicit"], p0["render"], device=dev)
+    f.set_cond(p0["cond"])
+    res = 256
+    f.sdf_grid([0.0, 0.0, 0.0], 1.8, 32)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    f.sdf_grid([0.0, 0.0, 0.0], 1.8, res)
+    e1.record()
+    torch.cuda.synchronize()
+    n = (res + 1) ** 3
+    dense = n / (e0.elapsed_time(e1) / 1000.0)
+    pts = (torch.rand(10000, 3, device=dev) - 0.5) * 2.0
+    f.implicit_forward(pts, want_feat=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(100):
+        f.implicit_forward(pts, want_feat=False)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"dense_res": res, "dense_points": n, "dense_points_per_s": dense,
+            "dense_tflops_algorithmic": dense * F_SDF / 1e12,
+            "batch_10k_points_per_s": 100 * 10000 / (e0.elapsed_time(e1) / 1000.0)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--engine", default=os.environ.get("MP_ENGINE", "tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,76 +381,51 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    from multiply_b200 import engine, parallel, _lib as L
+    from multiply_b200 import engine, parallel, scene as S, _lib as L
     lib = L.lib()
     engine.set_engine(args.engine)
-    sc, inp, hits = build_workload(rank, world)
+    # ---- workload: the drop-in scene (bodies from the device SMPL server) --------------------------------
+    sc, model, smpl_in = S.make_smpl_scene(P=PERSONS, S=S_SAMPLES, seed=42, device=dev)
+    full = S.make_rays(sc, RAYS_PER_GPU * world, seed=1234, region="boxes")
+    lo, hi = rank * RAYS_PER_GPU, (rank + 1) * RAYS_PER_GPU
+    inp = dict(uv=full["uv"][:, lo:hi].contiguous(), pose=full["pose"], intrinsics=full["intrinsics"])
+    hits = S.make_hit_lists(sc, inp)
     R = inp["uv"].shape[1]
     r = engine.Renderer(sc, device=dev)
-    # device-resident inputs (value) and pinned host inputs (e2e)
     d_inp = {k: v.to(dev) for k, v in inp.items()}
     d_hits = [h.to(dev) for h in hits]
-    h_inp = {k: v.pin_memory() for k, v in inp.items()}
-    h_hits = [h.pin_memory() for h in hits]
+    h_inp = {k: v.pin_memory() for k, v in dict(inp, **smpl_in).items()}
     h_out = torch.empty(R, 3).pin_memory()
-    gathered = torch.empty(world * R, 10 + PERSONS, device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    buf = parallel.PixelBuffer(R, PERSONS, dev)
+    gathered = torch.empty(world, R * (10 + PERSONS), device=dev) if world > 1 else None
+    timer = Timer(dev, world, lib)
+    model.output_buffers = buf.views          # the drop-in call writes its pixels straight into the gather buffer
 
     def step_resident():
-        o = r.render(d_inp, d_hits)
+        r.render(d_inp, d_hits, out=buf.views)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, parallel.pack_pixels(o))
-        return o
+            dist.all_gather_into_tensor(gathered, buf.flat)
 
     def step_e2e():
         di = {k: v.to(dev, non_blocking=True) for k, v in h_inp.items()}
-        dh = [h.to(dev, non_blocking=True) for h in h_hits]
-        o = r.render(di, dh)
+        o = model(di)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, parallel.pack_pixels(o))
+            dist.all_gather_into_tensor(gathered, buf.flat)
         h_out.copy_(o["rgb_values"], non_blocking=True)
-        return o
-
-    def timed(fn, steps, warmup, profile=False):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        lib.mp_launch_count(1)
-        if profile:
-            lib.mp_profile_enable(1)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for i in range(steps):
-            flush.fill_(i & 0xFF)          # L2 flush, outside the timed events
-            ev[i][0].record()
-            fn()
-            ev[i][1].record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        launches = lib.mp_launch_count(0)
-        if profile:
-            lib.mp_profile_enable(0)
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), int(launches)
 
     clocks = ClockSampler(local)
     clocks.start()
-    ms_value, launches = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_value, launches = timer.run(step_resident, args.steps, args.warmup)
+    with torch.no_grad():
+        ms_e2e, launches_e2e = timer.run(step_e2e, args.steps, args.warmup)
+    model._renderer.check_status()
     # Per-launch timing of the dominant kernel (roofline): CUDA events on the launching stream around every
     # tc_chain_kernel launch, in a pass of the same workload on the single-stream schedule.  (In the multi-stream
     # schedule the persons' launches queue behind each other INSIDE their event brackets, which would charge the
     # wait to the kernel.)
     prof_steps = max(1, min(args.steps, 20))
     L.check(lib.mp_set_streams(0), "mp_set_streams")
-    ms_serial, _ = timed(step_resident, prof_steps, 2, profile=True)
+    ms_serial, _ = timer.run(step_resident, prof_steps, 2, profile=True)
     import ctypes as C
     pms = (C.c_double * 4)()
     pl = (C.c_longlong * 4)()
@@ -249,10 +435,48 @@ def main():
     clocks.stop_flag = True
     clocks.join(timeout=2)
 
-    # one instrumented pass for parity + trip counts (outside timing)
+    # one instrumented pass for trip counts (outside timing)
     o = r.render(d_inp, d_hits, debug=True)
     torch.cuda.synchronize()
     trips = o["trips"].cpu().tolist()
+
+    # ---- parity at every N: the gathered frame against the same rays rendered on ONE GPU, and the drop-in call against
+    # the resident-input renderer on this rank's shard
+    parity = {}
+    with torch.no_grad():
+        o_drop = model({k: v.to(dev) for k, v in h_inp.items()})
+    torch.cuda.synchronize()
+    parity["drop_in_vs_resident_rgb_linf"] = linf(o_drop["rgb_values"], o["rgb_values"])
+    if world > 1:
+        step_resident()
+        torch.cuda.synchronize()
+        frame = parallel.PixelBuffer.frame(gathered, world, R, PERSONS)
+        if rank == 0:
+            fh = [h.to(dev) for h in S.make_hit_lists(sc, full)]
+            one = r.render({k: v.to(dev) for k, v in full.items()}, fh)
+            torch.cuda.synchronize()
+            parity["gathered_vs_single_gpu"] = {"bit_equal": all(torch.equal(frame[k], one[k]) for k in parallel.PIXEL_KEYS),
+                                                "rgb_linf": linf(frame["rgb_values"], one["rgb_values"]),
+                                                "normal_linf": linf(frame["normal_values"], one["normal_values"]),
+                                                "rays": R * world}
+
+    extras = {}
+    if not args.no_extras:
+        xs = max(3, min(args.steps, 10))
+        for name, fn in (("strong", lambda: extras_strong(timer, dev, rank, world, xs)),
+                         ("person_sharded", lambda: extras_person_sharded(timer, dev, rank, world, xs)),
+                         ("full_frame", lambda: extras_full_frame(dev, rank, world))):
+            try:
+                extras[name] = fn()
+            except Exception as e:          # a sub-record must never take the headline line down
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                if world > 1:
+                    raise
+        if rank == 0:
+            try:
+                extras["sdf_grid"] = extras_sdf_grid(dev)
+            except Exception as e:
+                extras["sdf_grid"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         total_rays = R * world
@@ -271,12 +495,14 @@ def main():
         for p in range(PERSONS):
             all_flops += hits[p].numel() * (trips[p] * E * F_SDF + n * (F_SDF + B_SDF + F_RGB))
         all_flops += R * 32 * F_BG
-        h2d = sum(v.numel() * v.element_size() for v in h_inp.values()) + sum(h.numel() * 8 for h in h_hits)
-        traffic = None
+        h2d = sum(v.numel() * v.element_size() for v in h_inp.values())
+        traffic, traffic_src = None, None
         for tag in ("r2", "r1"):
             tp = os.path.join(ROOT, "profiles", tag + "_traffic.json")
             if os.path.exists(tp):
-                traffic = json.load(open(tp))["tc_chain_kernel_dram_bytes_per_step"]
+                tj = json.load(open(tp))
+                traffic = tj["tc_chain_kernel_dram_bytes_per_step"]
+                traffic_src = "profiles/%s_traffic.json (%s)" % (tag, tj.get("captured", "ncu --set full capture of this workload"))
                 break
         line = {
             "metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -284,14 +510,18 @@ def main():
             "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split tensor-core operands, fp32 accumulate)",
             "data": "synthetic", "config": config_dict(world),
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(R * 3 * 4),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": "multiply_b200.model.multiply.Multiply.forward(input_dict): pinned-host inputs -> H2D -> "
+                            "SMPL server x%d -> posed-grid rebuild -> GPU ray/box culling -> sampler / deformer / MLPs / "
+                            "composite / background -> D2H rgb_values; no host synchronisation inside the call" % PERSONS,
+                    "gpu_launches_per_step": launches_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
-                         "traffic_note": "DRAM bytes of the kernel's launches of one step (ncu capture, profiles/); achieved is "
-                                         "likewise aggregated over the step's launches.  Algorithmic bytes are ~6.6 MB of weights "
-                                         "per field; the excess is the sigma' scratch of the reverse sweep spilling out of L2",
+                         "frac": ach / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic_note": "DRAM bytes of the kernel's launches of one step; achieved is likewise aggregated over "
+                                         "the step's launches.  Algorithmic bytes are ~6.6 MB of weights per field plus "
+                                         "~100 B of I/O per point",
                          "kernel": "tc_chain_kernel (fused SDF/grad/colour MLP chain)",
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "kernel_timing": "CUDA events per launch, %d-step pass on the single-stream schedule "
@@ -316,10 +546,9 @@ def main():
             tiles = pp[k] / 128.0
             issued += tiles * steps_nk[k] * 3 * 2.0 * 128 * 256 * 64
         line["roofline"]["issued_tensor_tflops"] = issued / (mlp_ms / 1000.0) / 1e12 if mlp_ms > 0 else 0.0
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             from oracle import port
-            from multiply_b200 import scene as S
-            n_sample = 48
+            n_sample = CPU_SAMPLE_RAYS
             sub = dict(uv=inp["uv"][:, :n_sample].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
             shits = S.make_hit_lists(sc, sub)
             tiny = dict(uv=inp["uv"][:, :8].contiguous(), pose=inp["pose"], intrinsics=inp["intrinsics"])
@@ -329,16 +558,17 @@ def main():
             ref = port.multiply_forward(sc, sub, shits)
             dt = time.time() - t0
             line["cpu_baseline"] = {"value": n_sample / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": "first %d rays of the same 4096-ray batch, full per-ray work "
+                                    "sample": "first %d rays of this rank's 4096-ray batch, timed once, full per-ray work "
                                               "(oracle/port.py, torch CPU fp32, %d threads)" % (n_sample, cores)}
             # parity of the same rays rendered inside the full batch is not comparable (batch-global sampler
             # flag): render the sample on the GPU and compare
             og = r.render(sub, shits)
             torch.cuda.synchronize()
-            line["parity"] = {"rgb_linf_vs_oracle": float((og["rgb_values"].cpu() - ref["rgb_values"]).abs().max()),
-                              "normal_linf_vs_oracle": float((og["normal_values"].cpu() - ref["normal_values"]).abs().max()),
-                              "acc_linf_vs_oracle": float((og["acc_map"].cpu() - ref["acc_map"]).abs().max()),
-                              "rays": n_sample}
+            parity.update({"rgb_linf_vs_oracle": linf(og["rgb_values"], ref["rgb_values"]),
+                           "normal_linf_vs_oracle": linf(og["normal_values"], ref["normal_values"]),
+                           "acc_linf_vs_oracle": linf(og["acc_map"], ref["acc_map"]), "rays": n_sample})
+        line["parity"] = parity
+        line["extras"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

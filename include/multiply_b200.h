@@ -118,6 +118,21 @@ int mp_implicit_forward_grad(mp_net_t* f, const float* x, int N, float* sdf, flo
 int mp_render_forward(mp_net_t* f, const float* points, const float* normals, const float* feat, int N,
                       float* rgb, void* workspace, size_t workspace_bytes, void* stream);
 size_t mp_mlp_workspace_bytes(int N);
+/* Background pair at given points (multiply.py:523-526): bg_implicit_network(pts [N,4], {'frame': code}) ->
+ * sdf [N] (may be NULL) and bg_rendering_network(None, None, view_dirs [N,3], None, feature, code) -> rgb [N,3].
+ * The frame code is the field's cond (mp_field_set_cond).  Workspace: mp_mlp_workspace_bytes(N). */
+int mp_bg_nets_forward(mp_net_t* bg_field, const float* pts, const float* view_dirs, int N, float* sdf, float* rgb,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Canonical SDF on the dense lattice of lib/utils/mesh.py:generate_mesh (:78-105; the values MISE's octree queries
+ * through Multiply.query_oc, multiply.py:169-172, batch by batch): values[(ix*(res+1)+iy)*(res+1)+iz] =
+ * ImplicitNet(p)[0] with p = ((idx/res - 0.5) * pad) * extent + centre (fp32, rounded step by step as numpy does;
+ * pad = 1.1, extent = the longest side of the SMPL bounds).  The pose conditioning is the field's cond
+ * (mp_field_set_cond).  The lattice is generated on the device and streamed through the sdf-only MLP program in
+ * 2^20-point slabs. */
+size_t mp_sdf_grid_workspace_bytes(int res);
+int mp_sdf_grid(mp_net_t* field, const float* center_host /*[3]*/, float extent, float pad, int res,
+                float* values /*[(res+1)^3]*/, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * deformer: SMPLDeformer (lib/model/deformer.py:6-89)
@@ -164,6 +179,13 @@ int mp_sphere_intersections(const float* cam_loc, const float* ray_dirs, int R, 
 int mp_ray_box_hits(const float* cam_loc, const float* ray_dirs, int R, const double* center_host,
                     const double* half_extent_host, const double* rot_dev, int64_t* idx_out, int* count_dev,
                     void* stream);
+/* multiply.py:262-263 on the device: an empty hit list becomes the single ray 0 (idx[0] = 0, *count_dev = 1). */
+int mp_hit_list_finalize(int64_t* idx, int* count_dev, void* stream);
+/* Same test with the box taken from the posed vertices on the device (no host read of the vertices): centre and half
+ * extents of the axis-aligned bounds of verts [V,3], inflated by `inflate` (1.2, multiply.py:212).  box_ws: >= 64 bytes
+ * of device scratch. */
+int mp_ray_aabb_hits(const float* cam_loc, const float* ray_dirs, int R, const float* verts, int V, double inflate,
+                     int64_t* idx_out, int* count_dev, void* box_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * SMPL server: SMPLServer.forward (lib/model/smpl.py:50-95) -> SMPL.forward (lib/smpl/body_models.py:278-364)
@@ -257,6 +279,10 @@ typedef struct {
   mp_net_t* bg_field;              /* NULL -> white background (multiply.py:540-541) */
   const int64_t* hit_index[MP_MAX_PERSONS]; /* device, sorted ray ids per person */
   int hit_count[MP_MAX_PERSONS];            /* >=1 (the reference substitutes ray 0 for an empty list) */
+  /* Optional device-side row counts (GPU culling without a host round trip, mp_ray_box_hits + mp_hit_list_finalize):
+   * when hit_count_dev[p] != NULL, hit_count[p] is the CAPACITY of hit_index[p] (normally R) and the number of valid
+   * rows is read on the device by every kernel of person p's branch.  NULL -> hit_count[p] is exact. */
+  const int* hit_count_dev[MP_MAX_PERSONS];
 } mp_scene_t;
 
 typedef struct {
@@ -272,6 +298,8 @@ typedef struct {
   float* normals[MP_MAX_PERSONS];
   int* trips;             /* device [P] or NULL */
   float* bg_T;            /* [R] or NULL */
+  int* status;            /* device int or NULL: bit 0 = some ray misses the bounding sphere (the reference prints
+                             'BOUNDING SPHERE PROBLEM' and exits, rend_util.py:140-142; its pixels are undefined here) */
 } mp_render_out_t;
 
 size_t mp_render_workspace_bytes(const mp_scene_t* scene, int R);

@@ -55,7 +55,8 @@ class Scene(C.Structure):
     _fields_ = [("sampler", SamplerCfg), ("P", C.c_int),
                 ("body", C.c_void_p * MP_MAX_PERSONS), ("field", C.c_void_p * MP_MAX_PERSONS),
                 ("bg_field", C.c_void_p),
-                ("hit_index", C.c_void_p * MP_MAX_PERSONS), ("hit_count", C.c_int * MP_MAX_PERSONS)]
+                ("hit_index", C.c_void_p * MP_MAX_PERSONS), ("hit_count", C.c_int * MP_MAX_PERSONS),
+                ("hit_count_dev", C.c_void_p * MP_MAX_PERSONS)]
 
 
 class RenderOut(C.Structure):
@@ -63,7 +64,7 @@ class RenderOut(C.Structure):
                 ("acc_map", C.c_void_p), ("acc_person_list", C.c_void_p),
                 ("z_vals", C.c_void_p * MP_MAX_PERSONS), ("sdf", C.c_void_p * MP_MAX_PERSONS),
                 ("rgb", C.c_void_p * MP_MAX_PERSONS), ("normals", C.c_void_p * MP_MAX_PERSONS),
-                ("trips", C.c_void_p), ("bg_T", C.c_void_p)]
+                ("trips", C.c_void_p), ("bg_T", C.c_void_p), ("status", C.c_void_p)]
 
 
 # name -> (restype, argtypes) ; mirrors include/multiply_b200.h one to one
@@ -88,6 +89,9 @@ SIGNATURES = {
     "mp_implicit_forward_grad": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mp_render_forward": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _SZ, _VP]),
     "mp_mlp_workspace_bytes": (_SZ, [_I]),
+    "mp_bg_nets_forward": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _SZ, _VP]),
+    "mp_sdf_grid_workspace_bytes": (_SZ, [_I]),
+    "mp_sdf_grid": (_I, [_VP, c_float_p, _F, _F, _I, _VP, _VP, _SZ, _VP]),
     "mp_body_bytes": (_SZ, [_I]),
     "mp_body_create": (_I, [_VP, _VP, _I, _F, _VP, _SZ, C.POINTER(_VP), _VP]),
     "mp_body_free": (None, [_VP]),
@@ -98,6 +102,8 @@ SIGNATURES = {
     "mp_camera_rays": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_sphere_intersections": (_I, [_VP, _VP, _I, _F, _VP, _VP, _VP]),
     "mp_ray_box_hits": (_I, [_VP, _VP, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _VP, _VP, _VP, _VP]),
+    "mp_hit_list_finalize": (_I, [_VP, _VP, _VP]),
+    "mp_ray_aabb_hits": (_I, [_VP, _VP, _I, _VP, _I, C.c_double, _VP, _VP, _VP, _VP]),
     "mp_smpl_bytes": (_SZ, [_I]),
     "mp_smpl_create": (_I, [_VP, _VP, _VP, _VP, C.POINTER(C.c_int), _VP, _I, _VP, _VP, _SZ, C.POINTER(_VP), _VP]),
     "mp_smpl_free": (None, [_VP]),

@@ -1,5 +1,6 @@
 // Shared declarations of the multiply_b200 CUDA library (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -13,7 +14,7 @@ namespace mp {
 // ---- error handling (no exceptions across the ABI) ----------------------------------------
 void set_error(const char* fmt, ...);
 extern thread_local char g_err[512];
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 
 #define MP_CHECK_CUDA(expr)                                                              \
   do {                                                                                   \
@@ -152,13 +153,13 @@ int simt_bg(const Field& f, const float* pts, const float* dirs, int N, float* s
             size_t ws_bytes, cudaStream_t st);
 int simt_render(const Field& f, const float* pts, const float* nrm, const float* feat, int N, float* rgb, void* ws,
                 size_t ws_bytes, cudaStream_t st);
-extern int g_engine;
+extern std::atomic<int> g_engine;
 
 // cross-file launchers
 int launch_deform_rays(const Body& b, const float* dirs, const float* cam, const float* z, int z_stride,
                        const int* zpos, int zpos_stride, int n_per_ray, int R, int prune, float* sdf_out,
                        int sdf_stride, float* xc_list, int* slot_list, int* count, uint8_t* outlier_out,
-                       const int* active, cudaStream_t st);
+                       const int* active, cudaStream_t st, const int* R_dev = nullptr);
 int launch_forward_jac(const Body& b, const float* x_c, int N, const int* n_dev, float* x_d, float* Jinv,
                        int jstride, cudaStream_t st);
 

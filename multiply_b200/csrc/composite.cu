@@ -26,7 +26,9 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
-__global__ void row_of_ray_kernel(const int64_t* __restrict__ idx, int n_rows, int* __restrict__ row_of_ray) {
+__global__ void row_of_ray_kernel(const int64_t* __restrict__ idx, int n_rows, int* __restrict__ row_of_ray,
+                                  const int* __restrict__ n_dev) {
+  if (n_dev) n_rows = min(n_rows, *n_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_rows) row_of_ray[idx[i]] = i;
 }
@@ -182,11 +184,11 @@ int launch_composite(const CompositePersons& cp, int R, int n, float beta, float
   return 0;
 }
 
-int launch_row_of_ray(const int64_t* idx, int n_rows, int R, int* row_of_ray, cudaStream_t st) {
+int launch_row_of_ray(const int64_t* idx, int n_rows, int R, int* row_of_ray, cudaStream_t st, const int* n_dev) {
   fill_int_kernel<<<div_up(R, 256), 256, 0, st>>>(row_of_ray, R, -1);
   MP_LAUNCH_CHECK();
   if (n_rows > 0) {
-    row_of_ray_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(idx, n_rows, row_of_ray);
+    row_of_ray_kernel<<<div_up(n_rows, 256), 256, 0, st>>>(idx, n_rows, row_of_ray, n_dev);
     MP_LAUNCH_CHECK();
   }
   return 0;
@@ -216,7 +218,7 @@ int mp_composite(const mp_person_samples_t* persons, int P, int R, int n, float 
   for (int p = 0; p < P; ++p) {
     int* ror = a.take<int>(R);
     MP_REQUIRE(a.ok, "mp_composite: workspace too small");
-    MP_TRY(mp::launch_row_of_ray(persons[p].ray_index, persons[p].n_rows, R, ror, st));
+    MP_TRY(mp::launch_row_of_ray(persons[p].ray_index, persons[p].n_rows, R, ror, st, nullptr));
     cp.n_rows[p] = persons[p].n_rows;
     cp.row_of_ray[p] = ror;
     cp.z[p] = persons[p].z_vals;

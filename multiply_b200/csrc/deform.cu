@@ -323,8 +323,9 @@ __global__ void deform_rays_kernel(Body b, const float* __restrict__ dirs, const
                                    int zpos_stride, int n_per_ray, int R, int prune, float* __restrict__ sdf_out,
                                    int sdf_stride, float* __restrict__ xc_list, int* __restrict__ slot_list,
                                    int* __restrict__ count, uint8_t* __restrict__ outlier_out,
-                                   const int* __restrict__ active) {
+                                   const int* __restrict__ active, const int* __restrict__ R_dev) {
   if (active && *active == 0) return;
+  if (R_dev) R = min(R, *R_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int total = R * n_per_ray;
   bool valid = i < total;
@@ -408,12 +409,12 @@ int body_build_grid(const float* verts, int V, float cell, int R0, GridHeader* h
 int launch_deform_rays(const Body& b, const float* dirs, const float* cam, const float* z, int z_stride,
                        const int* zpos, int zpos_stride, int n_per_ray, int R, int prune, float* sdf_out,
                        int sdf_stride, float* xc_list, int* slot_list, int* count, uint8_t* outlier_out,
-                       const int* active, cudaStream_t st) {
+                       const int* active, cudaStream_t st, const int* R_dev) {
   int total = R * n_per_ray;
   if (total <= 0) return 0;
   deform_rays_kernel<<<div_up(total, 128), 128, 0, st>>>(b, dirs, cam, z, z_stride, zpos, zpos_stride, n_per_ray, R,
                                                          prune, sdf_out, sdf_stride, xc_list, slot_list, count,
-                                                         outlier_out, active);
+                                                         outlier_out, active, R_dev);
   MP_LAUNCH_CHECK();
   return 0;
 }

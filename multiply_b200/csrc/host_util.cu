@@ -4,7 +4,7 @@
 
 namespace mp {
 thread_local char g_err[512] = {0};
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -13,14 +13,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// SM count of the CURRENT device (cached per device ordinal)
 int sm_count() {
-  static int n = -1;
-  if (n < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-    n = p.multiProcessorCount;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load();
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cache[dev].store(n);
   }
   return n;
 }
@@ -35,9 +36,7 @@ const char* mp_last_error(void) { return mp::g_err; }
 int mp_device_sm_count(void) { return mp::sm_count(); }
 
 long long mp_launch_count(int reset) {
-  long long v = mp::g_launches;
-  if (reset) mp::g_launches = 0;
-  return v;
+  return reset ? mp::g_launches.exchange(0) : mp::g_launches.load();
 }
 
 // torch.linspace CPU kernel (ATen RangeFactoriesKernel): step = (end-start)/(n-1);

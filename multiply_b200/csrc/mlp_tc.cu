@@ -22,6 +22,7 @@
 //     into colour layer 0, its extra inputs as a fifth K-block), RGB.
 #include "common.cuh"
 #include <vector>
+#include <mutex>
 #include <stdlib.h>
 
 namespace mp {
@@ -56,6 +57,8 @@ struct TcStep {
   int ncols;            // output columns that carry data (the rest are padding)
   int slot_off;         // first weight slot of this step in the blob
   int sc;               // index of this layer's 2^-s in inv_scale[]
+  int terms;            // split-precision terms of this step's products: 3 = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo (default),
+                        // 1 = A_hi.W_hi only (the lo weight slots are then neither loaded nor issued)
 };
 
 struct TcProgram {
@@ -93,14 +96,14 @@ struct TcIO {
 constexpr size_t kSigBytes = (size_t)8 * 64 * 128 * 16;      // sigma' [8][64][128] float4
 constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo chunks
 constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
-constexpr size_t kMiscBytes = (size_t)128 * 32 * 4;          // partial sums / normals [128][32]
 constexpr size_t kEmbBytes = (size_t)96 * 128 * 4;           // input embedding of the tile [E<=96][128]
-constexpr size_t kGe2Bytes = (size_t)96 * 128 * 4;           // d sdf / d embed through layer 0 [E<=96][128]
-constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes + kGe2Bytes;
+constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kEmbBytes;
 
 // shared memory carve-up
 constexpr int kABytes = 2 * 4 * 128 * 128;                   // hi + lo, 4 K-blocks of [128 x 128B]
-constexpr int kSmemBytes = kABytes + kRing * kSlotBytes + 256 + 1024;
+constexpr int kXchBytes = 3 * 128 * 4;                        // partial dots of column parts 1..3 (sdf), [3][128] floats
+constexpr int kSmemBytes = kABytes + kRing * kSlotBytes + 256 + kXchBytes + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA (227 KB)");
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -234,6 +237,22 @@ __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// The scratch lines of a tile are dead once read (sigma' and the stashed features are written once and read once):
+// `discard.global.L2` drops the line without write-back, so the dead lines neither travel to DRAM when they are
+// evicted nor compete for L2 capacity with the live part of the stash.  `dep` is a value computed FROM the loaded
+// data: the consumer instruction waits for the load of every lane of the warp, so the discard cannot overtake it.
+__device__ __forceinline__ void discard_line(const void* p, float dep) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p), "f"(dep) : "memory");
+}
+__device__ __forceinline__ void discard_line(const void* p, uint32_t dep) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p), "r"(dep) : "memory");
+}
+// asymmetric named barrier: producers arrive and run on, the consumer part waits
+template <int N>
+__device__ __forceinline__ void xbar_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void xbar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(N) : "memory"); }
+
 template <int N>
 __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
@@ -345,7 +364,7 @@ __device__ unsigned long long g_trace[4096];
 template <int NW, bool PIPE>
 __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
                                                                    const __grid_constant__ TcIO io) {
-  static_assert(!PIPE || NW == 16, "PIPE needs four column parts of 16-column chunks");
+  static_assert(PIPE && NW == 16, "the shipped kernel: four column parts of 16-column chunks, K-block-granular hand-over");
   constexpr int NBAR = PIPE ? 4 : 1;       // operand hand-over barriers (one per K-block when pipelined)
   constexpr int TCOLS = PIPE ? 512 : 256;  // TMEM columns
   constexpr int NPART = NW / 4;            // column parts
@@ -367,6 +386,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   uint64_t* x_free = bars + 2 * kRing + 1 + NBAR;      // K-block 0 of A drained by the MMAs (extra-input steps)
   uint64_t* x_ready = x_free + 1;                      // extra inputs staged there
   uint32_t* tmem_slot = (uint32_t*)(x_ready + 1);
+  float* xs = (float*)((char*)bars + 256);             // [3][128] partial sdf dots of column parts 1..3
 
   const int count = io.count ? min(io.cap, *io.count) : io.cap;
   const int ntiles = (count + 127) >> 7;
@@ -401,7 +421,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         for (int s = 0; s < P.nsteps; ++s) {
           const char* src = (const char*)P.blob + (size_t)P.step[s].slot_off * kSlotBytes;
           const int nslot = 2 * P.step[s].nk;
-          for (int j = 0; j < nslot; ++j, ++it) {
+          const int jstep = P.step[s].terms == 1 ? 2 : 1;     // single-term steps skip the W_lo slots
+          for (int j = 0; j < nslot; j += jstep, ++it) {
             int r = it % kRing;
             uint32_t ph = (it / kRing) & 1;
             mbar_wait(&empty[r], ph ^ 1);
@@ -424,6 +445,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             tc_fence_after();
           }
           const int nk = P.step[s].nk;
+          const bool one_term = P.step[s].terms == 1;
           const uint32_t tmem = tmem0 + (PIPE ? buf * 256u : 0u);
           uint32_t acc = 0;
           for (int kc = 0; kc < nk; ++kc) {
@@ -447,20 +469,22 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               uint64_t bd = make_desc(wb + ks * 32);
               umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), bd, idesc, acc);
               acc = 1;
-              umma_f16(tmem, make_desc(a_lo + (kc & 3) * 16384 + ks * 32), bd, idesc, 1);
+              if (!one_term) umma_f16(tmem, make_desc(a_lo + (kc & 3) * 16384 + ks * 32), bd, idesc, 1);
             }
             umma_commit(&empty[r]);
             ++it;
-            // lo slot: A_hi.W_lo
-            r = it % kRing;
-            mbar_wait(&full[r], (it / kRing) & 1);
-            tc_fence_after();
-            wb = smem_u32(ring + (size_t)r * kSlotBytes);
+            if (!one_term) {
+              // lo slot: A_hi.W_lo
+              r = it % kRing;
+              mbar_wait(&full[r], (it / kRing) & 1);
+              tc_fence_after();
+              wb = smem_u32(ring + (size_t)r * kSlotBytes);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-            umma_commit(&empty[r]);
-            ++it;
+              for (int ks = 0; ks < 4; ++ks)
+                umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+              umma_commit(&empty[r]);
+              ++it;
+            }
             if (kc == 0 && nk == 5) umma_commit(x_free);   // K-block 0 may be overwritten once these have completed
           }
           umma_commit(d_full);
@@ -485,9 +509,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     float4* sig = (float4*)scr;                                  // [8][64][128]
     uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
     float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
-    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
-    float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes);   // [96][128]
-    float* ge2 = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes);   // [96][128]
+    float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);    // [96][128]
     uint32_t df_ph = 0, xf_ph = 0;
     const int d = P.d_in, E = P.E;
     const int cbeg = part * PCOLS;
@@ -588,6 +610,31 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           fence_async_smem();
           mbar_arrive(x_ready);
         }
+        // Final step of the reverse sweep.  B0's output columns are permuted at pack time BY AXIS: column part a
+        // (a < d_in) holds, in its 16 columns of K-block 0, every embedding index that depends on x_a --
+        // [x_a, sin(2^0 x_a), cos(2^0 x_a), sin(2^1 x_a), ...] (embedders.py:8-34) -- so the chain rule
+        //   d sdf / d x_a = sum_k (g_k + skip_k) * d embed_k / d x_a
+        // of one axis runs inside one thread's registers, and the only exchange between warps is one float per row and
+        // axis through shared memory.  The skip gradient (parked at the F_SKIP_GRAD step) and the partner sin / cos of
+        // each index (parked by the tile prologue) are fetched before blocking on the accumulator.
+        const bool fin = (st.flags & F_FINAL_GRAD) != 0;
+        const bool fin_owner = fin && part < d;
+        constexpr int FN = 14;                         // indices per axis: 1 + 2 * multires <= 13 for multires <= 6 (+ pad)
+        float pg[FN], pe[FN];
+        if (fin_owner) {
+#pragma unroll
+          for (int j = 0; j < FN; ++j) {
+            // j = 0: x_a itself; j = 1 + 2 f: sin(2^f x_a); j = 2 + 2 f: cos(2^f x_a)
+            const int fq = (j - 1) >> 1;
+            const int k = (j == 0) ? part : d + 2 * fq * d + ((j - 1) & 1) * d + part;
+            const bool ok = j < 1 + 2 * P.multires;
+            pg[j] = ok ? ge[(size_t)k * 128 + row] : 0.f;
+            // partner: cos for a sin entry (+d), sin for a cos entry (-d)
+            pe[j] = (ok && j > 0) ? emb[(size_t)(((j - 1) & 1) ? k - d : k + d) * 128 + row] : 0.f;
+          }
+          if (part == 0 && io.jinv && valid)      // the inverse Jacobian is cold (written by the deformer kernel): pull it in
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(io.jinv + 12 * (size_t)pt));
+        }
         const bool tr = (io.knobs & 2) && blockIdx.x == 0 && warp == 2 && lane == 0 && tile == (int)(blockIdx.x + gridDim.x);
         unsigned long long* trp = g_trace + (P.nsteps > 12 ? 0 : 1024) + s * 8;
         if (tr) trp[0] = clock64();
@@ -611,6 +658,10 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
               *reinterpret_cast<uint4*>(A + o) = fh[u];
               *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
+              if ((lane & 7) == 0) {
+                discard_line(&fsc[(size_t)chunk * 128 + row], fh[u].x);
+                discard_line(&fsc[(size_t)(32 + chunk) * 128 + row], fl[u].x);
+              }
             }
           }
           arrive_all();
@@ -727,14 +778,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else if (st.epi == EPI_BWD) {
-            if (st.flags & F_FINAL_GRAD) {
-              // d / d embed of layer 0 (first E columns matter); the tail adds the parked skip gradient
-              if (c < 128) {
-#pragma unroll
-                for (int j = 0; j < CW; ++j)
-                  if (c + j < E) ge2[(size_t)(c + j) * 128 + row] = v[j] * isc;
-              }
-            } else if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
+            if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
               // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
               const float* s4f = reinterpret_cast<const float*>(s4);
 #pragma unroll
@@ -755,6 +799,11 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 v[4 * g4 + 2] *= isc * s4[g4].z;
                 v[4 * g4 + 3] *= isc * s4[g4].w;
               }
+            }
+            if (need_sig && (lane & 7) == 0) {   // this chunk's sigma' lines are dead: drop them from L2 without write-back
+#pragma unroll
+              for (int g4 = 0; g4 < G4; ++g4)
+                discard_line(&sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row], v[4 * g4]);
             }
             if (need_sig && ci + 1 < NCH) {   // next chunk's sigma' streams in behind the stores below
 #pragma unroll
@@ -806,120 +855,90 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             issue_next(ci);
           }
         };
-        // (a second register buffer for the TMEM reads was measured slower: +20 % kernel time from spills / code size)
-        tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
+        float gax = 0.f;                                // d sdf / d x_part (column parts 0..d-1, final step)
+        if (fin) {
+          // only column parts 0..d-1 have anything to drain, in their first chunk (the rest of B0's columns is padding)
+          if (fin_owner) {
+            tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
+            tmem_wait<CW>(va);
+#pragma unroll
+            for (int j = 0; j < FN; ++j) {
+              const float tot = fmaf(va[j], isc, pg[j]);             // through layer 0 + through the skip connection
+              const int fq = (j - 1) >> 1;
+              // d x / d x = 1 ; d sin(2^f x) = 2^f cos(2^f x) ; d cos(2^f x) = -2^f sin(2^f x)
+              const float w = (j == 0) ? 1.f : (float)(1 << fq) * (((j - 1) & 1) ? -pe[j] : pe[j]);
+              gax = fmaf(w, tot, gax);
+            }
+            if (tr) trp[2] = clock64();
+          }
+        } else {
+          // (a second register buffer for the TMEM reads was measured slower: +20 % kernel time from spills / code size)
+          tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
 #pragma unroll 1
-        for (int ci = 0; ci < NCH; ++ci) {
-          process_chunk(va, ci);
-          if (tr) trp[2 + ci] = clock64();
-          if (chunk_handover) {
-            // K-block ci of the next layer's operand is complete in this thread
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(&a_ready[ci]);
+          for (int ci = 0; ci < NCH; ++ci) {
+            process_chunk(va, ci);
+            if (tr) trp[2 + ci] = clock64();
+            if (chunk_handover) {
+              // K-block ci of the next layer's operand is complete in this thread
+              fence_async_smem();
+              tc_fence_before();
+              mbar_arrive(&a_ready[ci]);
+            }
           }
         }
         tc_fence_before();
         // ---- step-specific tails ----
         if (st.flags & F_SDF_DOT) {
-          misc[row * 32 + part] = dot0;
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (part == 0 && valid && io.sdf_out) {
-            float sacc = __ldg(P.b8);
+          // partial dots of column parts 1..3 -> shared memory; they arrive and run on, part 0 waits, sums in part
+          // order and writes the SDF.  (xs is next written a whole tile -- many barriers -- later.)
+          if (part != 0) {
+            xs[(part - 1) * 128 + row] = dot0;
+            xbar_arrive<NEPI>();
+          } else {
+            xbar_sync<NEPI>();
+            if (valid && io.sdf_out) {
+              float sacc = __ldg(P.b8) + dot0;
 #pragma unroll
-            for (int pp = 0; pp < NPART; ++pp) sacc += misc[row * 32 + pp];
-            io.sdf_out[slot] = sacc;
+              for (int pp = 0; pp < NPART - 1; ++pp) sacc += xs[pp * 128 + row];
+              io.sdf_out[slot] = sacc;
+            }
           }
-          // (no second barrier: these scratch slots are next written a whole tile -- many barriers -- later)
         }
         if (st.flags & F_SKIP_GRAD) __threadfence_block();
-        if (st.flags & F_FINAL_GRAD) {
+        if (fin) {
           if (tr) g_trace[513] = clock64();
-          // the inverse Jacobian of this row's point (cold: written by the deformer kernel) travels under the barriers
-          float4 ja = make_float4(0.f, 0.f, 0.f, 0.f), jb = ja, jc = ja;
-          if (io.jinv && valid) {
-            const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
-            ja = __ldg(J4);      // J[0..3]
-            jb = __ldg(J4 + 1);  // J[4..7]
-            jc = __ldg(J4 + 2);  // J[8..11]
-          }
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (tr) g_trace[514] = clock64();
-          // d sdf / d x = ge[0:d] + sum_f 2^f (cos(2^f x) ge_sin - sin(2^f x) ge_cos).  The (frequency, axis) pairs
-          // of a row are split over its column-part threads; sin / cos come back from the prologue's scratch.
-          // Everything here is an L2 round trip (the scratch was written by other warps): batches of five pairs
-          // keep 30 loads in flight instead of six.
-          {
-            float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
-            const int npair = d * P.multires;
-            constexpr int PB = 5;
-            for (int k0 = 0; k0 * NPART + part < npair; k0 += PB) {
-              float es[PB], ec[PB], gs[PB], gc[PB], hs[PB], hc[PB], fr[PB];
-              int ax[PB];
-#pragma unroll
-              for (int u = 0; u < PB; ++u) {
-                int pi = part + (k0 + u) * NPART;
-                const bool ok = pi < npair;
-                pi = ok ? pi : part;
-                const int f = pi / d, a = pi - f * d;
-                const size_t is = (size_t)(d + 2 * f * d + a) * 128 + row, ic = (size_t)(d + (2 * f + 1) * d + a) * 128 + row;
-                es[u] = emb[is]; ec[u] = emb[ic];
-                gs[u] = ge[is];  gc[u] = ge[ic];
-                hs[u] = ge2[is]; hc[u] = ge2[ic];
-                fr[u] = ok ? (float)(1 << f) : 0.f;
-                ax[u] = a;
-              }
-#pragma unroll
-              for (int u = 0; u < PB; ++u) {
-                const float term = fr[u] * (ec[u] * (gs[u] + hs[u]) - es[u] * (gc[u] + hc[u]));
-                gp0 += ax[u] == 0 ? term : 0.f;
-                gp1 += ax[u] == 1 ? term : 0.f;
-                gp2 += ax[u] == 2 ? term : 0.f;
-              }
-            }
-            if (part == 0) {
-              gp0 += ge[row] + ge2[row];
-              if (d > 1) gp1 += ge[128 + row] + ge2[128 + row];
-              if (d > 2) gp2 += ge[256 + row] + ge2[256 + row];
-            }
-            misc[row * 32 + 20 + part * 3 + 0] = gp0;
-            misc[row * 32 + 20 + part * 3 + 1] = gp1;
-            misc[row * 32 + 20 + part * 3 + 2] = gp2;
-          }
-          if (tr) g_trace[515] = clock64();
-          __threadfence_block();
-          ep_bar<NEPI>();
-          if (tr) g_trace[516] = clock64();
-          float g[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-          for (int pp = 0; pp < NPART; ++pp) {
-            g[0] += misc[row * 32 + 20 + pp * 3 + 0];
-            g[1] += misc[row * 32 + 20 + pp * 3 + 1];
-            g[2] += misc[row * 32 + 20 + pp * 3 + 2];
-          }
-          if (part == 0 && io.grad_out && valid) {
-            io.grad_out[3 * (size_t)pt] = g[0];
-            io.grad_out[3 * (size_t)pt + 1] = g[1];
-            io.grad_out[3 * (size_t)pt + 2] = g[2];
-          }
-          // every column part needs the normal as a colour input: all of them derive it (no second broadcast)
+          // axes 1..d-1 travel to column part 0 through shared memory (one float per row); it derives
+          // normal = normalize(g . J^-1) (multiply.py:661), normalised again with eps 1e-6 (:606), writes the outputs and
+          // is the part that stages the colour net's extra inputs [x_c, n].  Parts 1.. go on without waiting.
           float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-          if (io.jinv && valid) {
-            float v0 = g[0] * ja.x + g[1] * ja.w + g[2] * jb.z;
-            float v1 = g[0] * ja.y + g[1] * jb.x + g[2] * jb.w;
-            float v2 = g[0] * ja.z + g[1] * jb.y + g[2] * jc.x;
-            float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
-            const float inr = 1.f / nr;
-            v0 *= inr; v1 *= inr; v2 *= inr;
-            float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
-            const float in2 = 1.f / n2r;
-            n0 = v0 * in2; n1 = v1 * in2; n2 = v2 * in2;
-            if (part == 0 && io.nrm_out) {
-              io.nrm_out[3 * (size_t)slot] = n0;
-              io.nrm_out[3 * (size_t)slot + 1] = n1;
-              io.nrm_out[3 * (size_t)slot + 2] = n2;
+          if (fin_owner && part != 0) {
+            xs[(part - 1) * 128 + row] = gax;
+            asm volatile("bar.arrive 4, %0;" ::"r"(128 * d) : "memory");
+          } else if (part == 0) {
+            asm volatile("bar.sync 4, %0;" ::"r"(128 * d) : "memory");
+            const float gx0 = gax, gx1 = d > 1 ? xs[row] : 0.f, gx2 = d > 2 ? xs[128 + row] : 0.f;
+            if (io.grad_out && valid) {
+              io.grad_out[3 * (size_t)pt] = gx0;
+              io.grad_out[3 * (size_t)pt + 1] = gx1;
+              io.grad_out[3 * (size_t)pt + 2] = gx2;
+            }
+            if (io.jinv && valid) {
+              const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
+              const float4 ja = __ldg(J4), jb = __ldg(J4 + 1), jc = __ldg(J4 + 2);      // J[0..3], J[4..7], J[8..11]
+              float v0 = gx0 * ja.x + gx1 * ja.w + gx2 * jb.z;
+              float v1 = gx0 * ja.y + gx1 * jb.x + gx2 * jb.w;
+              float v2 = gx0 * ja.z + gx1 * jb.y + gx2 * jc.x;
+              float nr = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-12f);     // multiply.py:661
+              const float inr = 1.f / nr;
+              v0 *= inr; v1 *= inr; v2 *= inr;
+              float n2r = fmaxf(sqrtf(v0 * v0 + v1 * v1 + v2 * v2), 1e-6f);     // multiply.py:606
+              const float in2 = 1.f / n2r;
+              n0 = v0 * in2; n1 = v1 * in2; n2 = v2 * in2;
+              if (io.nrm_out) {
+                io.nrm_out[3 * (size_t)slot] = n0;
+                io.nrm_out[3 * (size_t)slot + 1] = n1;
+                io.nrm_out[3 * (size_t)slot + 2] = n2;
+              }
             }
           }
           nrm[0] = n0;
@@ -929,19 +948,25 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         }
         if (st.flags & F_RGB_OUT) {
           // last step of the tile: the MMAs are done with A, its K-block 3 serves as the exchange buffer for the
-          // partial dots (the next write there is a whole layer step -- and several barriers -- away)
+          // partial dots (the next write there is a whole layer step -- and several barriers -- away); parts 1..3 arrive
+          // and go on to the next tile's prologue, part 0 sums in part order
           float* xch = reinterpret_cast<float*>(A + 3 * 16384);
-          xch[(part * 3 + 0) * 128 + row] = dot0;
-          xch[(part * 3 + 1) * 128 + row] = dot1;
-          xch[(part * 3 + 2) * 128 + row] = dot2;
-          ep_bar<NEPI>();
-          if (part == 0 && valid && io.rgb_out) {
+          if (part != 0) {
+            xch[(part * 3 + 0) * 128 + row] = dot0;
+            xch[(part * 3 + 1) * 128 + row] = dot1;
+            xch[(part * 3 + 2) * 128 + row] = dot2;
+            asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
+          } else {
+            asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
+            if (valid && io.rgb_out) {
+              const float dk[3] = {dot0, dot1, dot2};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              float z = __ldg(P.brgb + k);
+              for (int k = 0; k < 3; ++k) {
+                float z = __ldg(P.brgb + k) + dk[k];
 #pragma unroll
-              for (int pp = 0; pp < NPART; ++pp) z += xch[(pp * 3 + k) * 128 + row];
-              io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
+                for (int pp = 1; pp < NPART; ++pp) z += xch[(pp * 3 + k) * 128 + row];
+                io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
+              }
             }
           }
         }
@@ -974,7 +999,7 @@ struct TcBlob {
   bool has_full;
 };
 
-__global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restrict__ out) {
+__global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restrict__ out, float rz_comp) {
   __shared__ float s[256];
   float m = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
@@ -991,7 +1016,7 @@ __global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restr
     if (mx > 0.f) frexpf(mx, &ex);       // mx = f * 2^ex, f in [0.5,1)
     float sc = ldexpf(1.f, 14 - ex);
     out[0] = sc;
-    out[1] = 1.f / sc;
+    out[1] = (1.f / sc) * (1.f + rz_comp);
   }
 }
 
@@ -1000,14 +1025,27 @@ __global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restr
 //   transposed == 1 : B[n][k] = W[(k_off + kc*64 + k) * ld + n_off + n]
 __global__ void pack_slot_kernel(const float* __restrict__ W, int ld, int transposed, int n_off, int k_off,
                                  int n_valid, int k_valid, int kc, const float* __restrict__ scale,
-                                 uint8_t* __restrict__ dst_hi, uint8_t* __restrict__ dst_lo) {
+                                 uint8_t* __restrict__ dst_hi, uint8_t* __restrict__ dst_lo, int perm16) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 256 * 64) return;
   int n = idx >> 6, k = idx & 63;
   int kk = kc * 64 + k;
+  // perm16 = d_in > 0 (final step of the reverse sweep): output column a * 16 + j (a < d_in) carries the embedding index
+  // of axis a in the order [x_a, sin(2^0 x_a), cos(2^0 x_a), sin(2^1 x_a), ...] (embedders.py:8-34), i.e.
+  // j = 0 -> a ; j = 1 + 2 f + t -> d + 2 f d + t d + a ; every other column is padding.  Column part a of the epilogue
+  // owns columns [16 a, 16 a + 16) of K-block 0, so it holds every term of d sdf / d x_a.
+  int ns = n;
+  if (perm16) {
+    const int dd = perm16, a = n >> 4, j = n & 15;
+    ns = n_valid;
+    if (n < 64 && a < dd) {
+      const int k = (j == 0) ? a : dd + ((j - 1) >> 1) * 2 * dd + ((j - 1) & 1) * dd + a;
+      if (k < n_valid) ns = k;
+    }
+  }
   float w = 0.f;
-  if (n < n_valid && kk < k_valid)
-    w = transposed ? W[(size_t)(k_off + kk) * ld + n_off + n] : W[(size_t)(n_off + n) * ld + k_off + kk];
+  if (ns < n_valid && kk < k_valid)
+    w = transposed ? W[(size_t)(k_off + kk) * ld + n_off + ns] : W[(size_t)(n_off + ns) * ld + k_off + kk];
   w *= scale[0];
   __half h = __float2half_rn(w);
   __half l = __float2half_rn(w - __half2float(h));
@@ -1073,19 +1111,25 @@ struct PackCtx {
 };
 
 static int pack_layer(PackCtx& c, TcStep& stp, const float* W, int ld, int transposed, int n_off, int k_off,
-                      int n_valid, int k_valid, int nk, int total_elems) {
+                      int n_valid, int k_valid, int nk, int total_elems, int perm16 = 0) {
   const int first = c.nslots;
   const int step = c.nlayers++;
   stp.slot_off = first;
   stp.sc = step;
+  stp.terms = 3;
   if (c.rc) return first;
-  absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step);
+  static float rz_comp = -1.f;
+  if (rz_comp < 0.f) {
+    const char* e = getenv("MP_TC_RZ_COMP");      // experiment knob: relative compensation of the accumulator truncation
+    rz_comp = e ? (float)atof(e) : 0.f;
+  }
+  absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step, rz_comp);
   g_launches++;
   for (int kc = 0; kc < nk; ++kc) {
     uint8_t* hi = c.blob + (size_t)c.nslots * kSlotBytes;
     uint8_t* lo = hi + kSlotBytes;
     pack_slot_kernel<<<64, 256, 0, c.st>>>(W, ld, transposed, n_off, k_off, n_valid, k_valid, kc,
-                                           c.scales + 2 * step, hi, lo);
+                                           c.scales + 2 * step, hi, lo, perm16);
     g_launches++;
     c.nslots += 2;
   }
@@ -1228,7 +1272,9 @@ int tc_pack(Field& f, Arena& a, cudaStream_t st) {
       ++s;
     }
     // ---- B0: d/d embed = (g_0 * sigma'_0) . W0[:, :E] ----
-    pack_layer(c, P.step[s], f.imp_W[0], f.imp_in[0], 1, 0, 0, E, 256, 4, 256 * f.imp_in[0]);
+    MP_REQUIRE(f.d_in <= 4 && 1 + 2 * f.multires <= 14,
+               "tc_pack: the final-gradient step keeps 1 + 2 * multires <= 14 embedding columns per axis");
+    pack_layer(c, P.step[s], f.imp_W[0], f.imp_in[0], 1, 0, 0, E, 256, 4, 256 * f.imp_in[0], /*perm16=*/f.d_in);
     P.step[s].nk = 4;
     P.step[s].epi = EPI_BWD;
     P.step[s].flags = F_FINAL_GRAD;
@@ -1281,13 +1327,17 @@ struct ProfEntry {
   int cap;
   int* host_count; // pinned
 };
-static bool g_prof_on = false;
+// The profile is a process-wide diagnostic (bench.py): its state is guarded by g_prof_mu so that concurrent
+// launches from several host threads stay well defined.
+static std::mutex g_prof_mu;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfEntry>* g_prof = nullptr;
 static int* g_prof_pinned = nullptr;
 static int g_prof_used = 0;
 constexpr int kProfMax = 1 << 16;
 
 int prof_enable(int on) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
   if (on && !g_prof) {
     g_prof = new std::vector<ProfEntry>();
     MP_CHECK_CUDA(cudaMallocHost(&g_prof_pinned, kProfMax * sizeof(int)));
@@ -1301,6 +1351,7 @@ int prof_read(double* ms, long long* launches, double* points, int reset) {
     launches[k] = 0;
     points[k] = 0;
   }
+  std::lock_guard<std::mutex> g(g_prof_mu);
   if (!g_prof) return 0;
   for (auto& e : *g_prof) {
     MP_CHECK_CUDA(cudaEventSynchronize(e.e1));
@@ -1347,21 +1398,22 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
     }
     io.knobs = knobs;
   }
-  static bool attr_set = false;
-  static int nw = 16;
-  static int pipe = 1; // K-block-granular hand-over with two accumulators (MP_TC_PIPE=0: whole-layer hand-over)
-  if (!attr_set) {
-    const char* e = getenv("MP_TC_EPI_WARPS");
-    if (e && atoi(e) == 8) nw = 8;
-    const char* e3 = getenv("MP_TC_PIPE");
-    if (e3) pipe = atoi(e3);
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  {
+    // the > 48 KB dynamic shared memory opt-in is per device
+    static std::mutex attr_mu;
+    static unsigned long long attr_done = 0;      // bit d: cudaFuncSetAttribute done on device d
+    int dev = 0;
+    MP_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(attr_mu);
+    if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
+      MP_CHECK_CUDA(cudaFuncSetAttribute(tc_chain_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
+    }
   }
   ProfEntry pe;
-  const bool prof = g_prof_on && g_prof && g_prof_used < kProfMax;
+  std::unique_lock<std::mutex> prof_lock(g_prof_mu, std::defer_lock);
+  if (g_prof_on.load()) prof_lock.lock();
+  const bool prof = prof_lock.owns_lock() && g_prof_on.load() && g_prof && g_prof_used < kProfMax;
   if (prof) {
     MP_CHECK_CUDA(cudaEventCreate(&pe.e0));
     MP_CHECK_CUDA(cudaEventCreate(&pe.e1));
@@ -1374,12 +1426,7 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
     }
     MP_CHECK_CUDA(cudaEventRecord(pe.e0, st));
   }
-  if (nw == 16 && pipe)
-    tc_chain_kernel<16, true><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
-  else if (nw == 16)
-    tc_chain_kernel<16, false><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
-  else
-    tc_chain_kernel<8, false><<<grid, 64 + 32 * 8, kSmemBytes, st>>>(P, io);
+  tc_chain_kernel<16, true><<<grid, 64 + 32 * 16, kSmemBytes, st>>>(P, io);
   MP_LAUNCH_CHECK();
   if (prof) {
     MP_CHECK_CUDA(cudaEventRecord(pe.e1, st));

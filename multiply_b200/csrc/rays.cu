@@ -66,12 +66,17 @@ __global__ void sphere_kernel(const float* __restrict__ cam, const float* __rest
 __global__ void __launch_bounds__(1024) ray_box_hits_kernel(const float* __restrict__ cam, const float* __restrict__ dirs,
                                                             int R, double cx, double cy, double cz, double hx, double hy,
                                                             double hz, const double* __restrict__ rot,
-                                                            int64_t* __restrict__ idx_out, int* __restrict__ count) {
+                                                            int64_t* __restrict__ idx_out, int* __restrict__ count,
+                                                            const double* __restrict__ box_dev, int finalize) {
   __shared__ int s_warp[32];
   __shared__ int s_base, s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
+  if (box_dev) {     // centre / half extents computed on the device (aabb_kernel)
+    cx = box_dev[0]; cy = box_dev[1]; cz = box_dev[2];
+    hx = box_dev[3]; hy = box_dev[4]; hz = box_dev[5];
+  }
   double Rm[9];
   for (int k = 0; k < 9; ++k) Rm[k] = rot ? rot[k] : ((k % 4 == 0) ? 1.0 : 0.0);
   for (int r0 = 0; r0 < R; r0 += blockDim.x) {
@@ -112,7 +117,54 @@ __global__ void __launch_bounds__(1024) ray_box_hits_kernel(const float* __restr
     if (tid == 0) s_base += s_total;
     __syncthreads();
   }
-  if (tid == 0 && count) *count = s_base;
+  if (tid == 0 && count) {
+    if (finalize && s_base == 0) {     // multiply.py:262-263: an empty hit list becomes the single ray 0
+      idx_out[0] = 0;
+      s_base = 1;
+    }
+    *count = s_base;
+  }
+}
+
+// centre and inflated half extents of the axis-aligned bounds of verts [V,3] (one CTA; fp64 like the host code)
+__global__ void __launch_bounds__(1024) aabb_kernel(const float* __restrict__ verts, int V, double inflate,
+                                                    double* __restrict__ box) {
+  __shared__ float s_lo[3][32], s_hi[3][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int v = tid; v < V; v += blockDim.x)
+    for (int k = 0; k < 3; ++k) {
+      float x = verts[3 * v + k];
+      lo[k] = fminf(lo[k], x);
+      hi[k] = fmaxf(hi[k], x);
+    }
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    if (lane == 0) {
+      s_lo[k][warp] = lo[k];
+      s_hi[k][warp] = hi[k];
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float l = 3.4e38f, h = -3.4e38f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      l = fminf(l, s_lo[tid][w]);
+      h = fmaxf(h, s_hi[tid][w]);
+    }
+    box[tid] = ((double)l + (double)h) / 2.0;
+    box[3 + tid] = ((double)h - (double)l) / 2.0 * inflate;
+  }
+}
+
+__global__ void hit_list_finalize_kernel(int64_t* __restrict__ idx, int* __restrict__ count) {
+  if (*count == 0) {
+    idx[0] = 0;
+    *count = 1;
+  }
 }
 
 __global__ void density_kernel(const float* __restrict__ sdf, int N, float beta, float* __restrict__ out) {
@@ -151,7 +203,29 @@ int mp_ray_box_hits(const float* cam_loc, const float* ray_dirs, int R, const do
   mp::ray_box_hits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cam_loc, ray_dirs, R, center_host[0], center_host[1],
                                                                center_host[2], half_extent_host[0],
                                                                half_extent_host[1], half_extent_host[2], rot_dev,
-                                                               idx_out, count_dev);
+                                                               idx_out, count_dev, nullptr, 0);
+  MP_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_hit_list_finalize(int64_t* idx, int* count_dev, void* stream) {
+  MP_REQUIRE(idx && count_dev, "mp_hit_list_finalize: null argument");
+  mp::hit_list_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(idx, count_dev);
+  MP_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_ray_aabb_hits(const float* cam_loc, const float* ray_dirs, int R, const float* verts, int V, double inflate,
+                     int64_t* idx_out, int* count_dev, void* box_ws, void* stream) {
+  MP_REQUIRE(cam_loc && ray_dirs && verts && idx_out && count_dev && box_ws, "mp_ray_aabb_hits: null argument");
+  MP_REQUIRE(V > 0, "mp_ray_aabb_hits: V must be positive");
+  if (R <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  mp::aabb_kernel<<<1, 1024, 0, st>>>(verts, V, inflate, (double*)box_ws);
+  MP_LAUNCH_CHECK();
+  // the hit list comes out finalised (multiply.py:262-263): empty -> ray 0
+  mp::ray_box_hits_kernel<<<1, 1024, 0, st>>>(cam_loc, ray_dirs, R, 0, 0, 0, 0, 0, 0, nullptr, idx_out, count_dev,
+                                              (const double*)box_ws, 1);
   MP_LAUNCH_CHECK();
   return 0;
 }

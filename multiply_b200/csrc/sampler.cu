@@ -68,8 +68,9 @@ __global__ void tables_kernel(SamplerTables t, int E, int S, int X, int max_iter
 __global__ void sampler_init_kernel(const float* __restrict__ dirs, const float* __restrict__ cam, int R, float r,
                                     float near, int E, const float* __restrict__ tvals, float bound_coef,
                                     float* __restrict__ z, int zcap, float* __restrict__ beta,
-                                    float* __restrict__ far_out, SamplerState* st) {
+                                    float* __restrict__ far_out, SamplerState* st, const int* __restrict__ R_dev) {
   int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (R_dev) R = min(R, *R_dev);     // device-side row count (hit list culled on the GPU, no host sync)
   if (ray >= R) return;
   const float* o = cam + 3 * ray;
   const float* d = dirs + 3 * ray;
@@ -151,11 +152,13 @@ __device__ float error_bound_warp(const float* sz, const float* ss, const float*
 // Beta line search of one trip     ray_sampler.py:94-122, :137
 __global__ void sampler_beta_kernel(const float* __restrict__ z, const float* __restrict__ sdf, int zcap, int M,
                                     int R, float beta0, float eps, int beta_iters, int trip,
-                                    float* __restrict__ beta_state, SamplerState* st, int mmax) {
+                                    float* __restrict__ beta_state, SamplerState* st, int mmax,
+                                    const int* __restrict__ R_dev) {
   if (st->active[trip] == 0) return;
   extern __shared__ float smem[];
   int wpc = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int ray = blockIdx.x * wpc + wid;
+  if (R_dev) R = min(R, *R_dev);
   if (ray >= R) return;
   float* sz = smem + (size_t)wid * 3 * mmax;
   float* ss = sz + mmax;
@@ -210,8 +213,9 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
                                         const float* __restrict__ far, SamplerTables tab,
                                         float* __restrict__ z_out, float* __restrict__ sdf_out,
                                         int* __restrict__ pos_new, float* __restrict__ z_final,
-                                        SamplerState* st, int mmax) {
+                                        SamplerState* st, int mmax, const int* __restrict__ R_dev) {
   if (st->active[trip] == 0) return;
+  if (R_dev) R = min(R, *R_dev);
   const bool cont = (st->not_converge[trip] != 0) && (trip + 1 < max_iters);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (trip + 1 < 8) st->active[trip + 1] = cont ? 1 : 0;
@@ -398,7 +402,7 @@ static bool sampler_carve(Arena& a, const mp_sampler_cfg_t& c, int R, SamplerWs&
 // The whole Algorithm-1 loop for one person.  z_final [R, S+X+2].
 int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field, const float* dirs,
                 const float* cam, int R, float* z_final, float* z_bg, int* trips_out, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, const int* R_dev) {
   const int E = c.N_samples_eval, S = c.N_samples, X = c.N_samples_extra;
   MP_REQUIRE(E >= 2 && S >= 1 && X >= 0 && c.max_total_iters >= 1 && c.max_total_iters <= 8,
              "sampler: unsupported configuration (E=%d S=%d X=%d iters=%d)", E, S, X, c.max_total_iters);
@@ -415,7 +419,7 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
                                                  (float)(1.0 / c.scene_bounding_sphere), w.st);
   MP_LAUNCH_CHECK();
   sampler_init_kernel<<<div_up(R, 128), 128, 0, st>>>(dirs, cam, R, c.scene_bounding_sphere, c.near, E, w.tab.u_E,
-                                                      bound_coef, w.zA, zcap, w.beta, w.far, w.st);
+                                                      bound_coef, w.zA, zcap, w.beta, w.far, w.st, R_dev);
   MP_LAUNCH_CHECK();
   float *zc = w.zA, *zn = w.zB, *sc = w.sA, *sn = w.sB;
   const int mmax = zcap;
@@ -435,7 +439,7 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
     const int M = (t + 1) * E;
     // SDF of the E new samples of every ray (multiply.py:137-151 under no_grad, ray_sampler.py:82-88)
     MP_TRY(launch_deform_rays(body, dirs, cam, zc, zcap, t == 0 ? nullptr : w.pos_new, E, E, R, /*prune=*/1, sc,
-                              zcap, w.xc_list, w.slot_list, &w.st->count[t], nullptr, &w.st->active[t], st));
+                              zcap, w.xc_list, w.slot_list, &w.st->count[t], nullptr, &w.st->active[t], st, R_dev));
     MP_TRY(field_sdf_list(field, w.xc_list, w.slot_list, &w.st->count[t], R * E, sc, w.mlp_ws, w.mlp_ws_bytes, st));
     // shared memory per ray sized for THIS trip's list (M = (t+1) E entries; the final-set staging needs X + 2):
     // trip 0 -- usually the only active one -- then keeps every ray of the batch resident at once instead of
@@ -445,11 +449,11 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
     const int wb = min(wpc_for_trip, clamp_wpc((size_t)(200 * 1024) / pw_b));
     const int wr = min(wpc_for_trip, clamp_wpc((size_t)(200 * 1024) / pw_r));
     sampler_beta_kernel<<<div_up(R, wb), wb * 32, wb * pw_b, st>>>(
-        zc, sc, zcap, M, R, beta0, c.eps, c.beta_iters, t, w.beta, w.st, stride);
+        zc, sc, zcap, M, R, beta0, c.eps, c.beta_iters, t, w.beta, w.st, stride, R_dev);
     MP_LAUNCH_CHECK();
     sampler_resample_kernel<<<div_up(R, wr), wr * 32, wr * pw_r, st>>>(
         zc, sc, zcap, M, R, E, S, X, c.max_total_iters, c.add_tiny, c.near, t, w.beta, w.far, w.tab, zn, sn,
-        w.pos_new, z_final, w.st, stride);
+        w.pos_new, z_final, w.st, stride, R_dev);
     MP_LAUNCH_CHECK();
     float* tz = zc; zc = zn; zn = tz;
     float* ts = sc; sc = sn; sn = ts;
@@ -487,6 +491,6 @@ int mp_sample_rays(const mp_sampler_cfg_t* cfg, mp_body_t* body, mp_net_t* field
   MP_REQUIRE(cfg && body && field && ray_dirs && cam_loc && z_vals, "mp_sample_rays: null argument");
   MP_REQUIRE(body->b.tfs, "mp_sample_rays: body has no pose (call mp_body_set_pose)");
   return mp::sample_rays(*cfg, body->b, field->f, ray_dirs, cam_loc, R, z_vals, z_bg, trips_out, workspace,
-                         workspace_bytes, (cudaStream_t)stream);
+                         workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 }

@@ -106,6 +106,29 @@ class Field:
                                         ws.numel(), L.stream_ptr()), "mp_implicit_forward")
         return sdf, feat
 
+    def sdf_grid(self, center, extent, res, pad=1.1):
+        """Canonical SDF on the (res+1)^3 lattice of generate_mesh (lib/utils/mesh.py:78-105): returns [res+1]*3 fp32."""
+        lib = L.lib()
+        n1 = res + 1
+        vals = torch.empty(n1, n1, n1, device=self.device)
+        ws = torch.empty(lib.mp_sdf_grid_workspace_bytes(res), dtype=torch.uint8, device=self.device)
+        c = (C.c_float * 3)(*[float(v) for v in center])
+        L.check(lib.mp_sdf_grid(self.handle, c, float(extent), float(pad), int(res), vals.data_ptr(), ws.data_ptr(),
+                                ws.numel(), L.stream_ptr()), "mp_sdf_grid")
+        return vals
+
+    def bg_forward(self, pts, view_dirs):
+        """Background pair at given points (multiply.py:523-526): pts [N,4], view_dirs [N,3] -> (sdf [N], rgb [N,3])."""
+        lib = L.lib()
+        pts, view_dirs = _dev(pts, self.device), _dev(view_dirs, self.device)
+        N = pts.shape[0]
+        sdf = torch.empty(N, device=self.device)
+        rgb = torch.empty(N, 3, device=self.device)
+        ws = torch.empty(lib.mp_mlp_workspace_bytes(N), dtype=torch.uint8, device=self.device)
+        L.check(lib.mp_bg_nets_forward(self.handle, pts.data_ptr(), view_dirs.data_ptr(), N, sdf.data_ptr(),
+                                       rgb.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr()), "mp_bg_nets_forward")
+        return sdf, rgb
+
     def render_forward(self, points, normals, feat):
         lib = L.lib()
         points, normals, feat = (_dev(t, self.device) for t in (points, normals, feat))
@@ -188,10 +211,21 @@ class Renderer:
 
     def __init__(self, scene, device="cuda"):
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        device = self.device
         self.cfg = scene["cfg"]
         self.beta_param = float(scene["beta_param"])
+        self.beta_min = float(scene.get("beta_min", 1e-4))
         self.P = len(scene["persons"])
         self.fields, self.bodies = [], []
+        with torch.cuda.device(self.device):
+            self._build(scene, device)
+        self._ws = None
+        self._status = None
+        self.n = self.cfg["N_samples"] + self.cfg["N_samples_extra"] + 1
+
+    def _build(self, scene, device):
         for person in scene["persons"]:
             f = Field(person["implicit"], person["render"], background=False, device=device)
             f.set_cond(person["cond"])
@@ -204,74 +238,127 @@ class Renderer:
         if scene.get("bg_implicit") is not None:
             self.bg = Field(scene["bg_implicit"], scene["bg_render"], background=True, device=device)
             self.bg.set_cond(scene["frame_code"])
-        self._ws = None
-        self.n = self.cfg["N_samples"] + self.cfg["N_samples_extra"] + 1
 
     def update_person(self, p, person):
         """New pose for person p (per-frame update): cond, posed vertices, bone transforms."""
-        self.fields[p].set_cond(person["cond"])
-        self.bodies[p].set_pose(person["verts_p"], person["tfs"])
+        with torch.cuda.device(self.device):
+            self.fields[p].set_cond(person["cond"])
+            self.bodies[p].set_pose(person["verts_p"], person["tfs"])
 
-    def render(self, inputs, hit_lists, debug=False):
+    def check_status(self):
+        """Raises if the last render saw a ray that misses the bounding sphere — where the reference prints
+        'BOUNDING SPHERE PROBLEM!' and exits (rend_util.py:140-142).  Reads one device int (synchronises)."""
+        if self._status is not None and int(self._status.item()) & 1:
+            raise RuntimeError("BOUNDING SPHERE PROBLEM! (a camera ray misses the r=%g scene sphere)"
+                               % self.cfg["scene_bounding_sphere"])
+
+    def render(self, inputs, hit_lists, debug=False, persons=None, check=False, out=None):
         """inputs: uv [1,R,2], pose [1,4,4], intrinsics [1,4,4] (CUDA or CPU tensors);
-        hit_lists: per person int64 ray ids (empty list -> ray 0, multiply.py:262-263).
+        hit_lists: per rendered person either an int64 tensor of ray ids (empty -> ray 0, multiply.py:262-263) or a
+        pair (ids [R] int64 on the device, count [1] int32 on the device) as produced by ``ray_aabb_hits`` — the
+        count then never visits the host;
+        persons: indices of the persons to render (default: all; ``Multiply.forward(input, id=p)`` passes [p],
+        multiply.py:244-247) — ``acc_person_list`` has one column per rendered person;
+        check: read the bounding-sphere status flag after the call (synchronises) and raise like the reference;
+        out: optional dict of preallocated contiguous output tensors (e.g. ``parallel.PixelBuffer.views``).
         Returns the eval output dict of Multiply.forward (multiply.py:589-598)."""
+        with torch.cuda.device(self.device):
+            return self._render(inputs, hit_lists, debug, persons, check, out)
+
+    def _render(self, inputs, hit_lists, debug, persons, check, out_bufs=None):
         lib = L.lib()
         dev = self.device
         uv = _dev(inputs["uv"].reshape(-1, 2), dev)
         pose = _dev(inputs["pose"].reshape(4, 4), dev)
         K = _dev(inputs["intrinsics"].reshape(4, 4), dev)
         R = uv.shape[0]
+        plist = list(range(self.P)) if persons is None else [int(p) for p in persons]
+        Pn = len(plist)
+        assert len(hit_lists) == Pn, "one hit list per rendered person"
         sc = L.Scene()
-        sc.sampler = sampler_cfg(self.cfg, self.beta_param)
-        sc.P = self.P
+        sc.sampler = sampler_cfg(self.cfg, self.beta_param, self.beta_min)
+        sc.P = Pn
         hits = []
-        for p in range(self.P):
-            h = hit_lists[p]
-            if h.numel() == 0:
+        dev_counts = False
+        for k, p in enumerate(plist):
+            h = hit_lists[k]
+            cnt = None
+            if isinstance(h, (tuple, list)):
+                h, cnt = h
+                assert h.is_cuda and cnt.is_cuda and h.dtype == torch.int64 and cnt.dtype == torch.int32
+                dev_counts = True
+            elif h.numel() == 0:
                 h = torch.zeros(1, dtype=torch.int64)
             h = h.to(device=dev, dtype=torch.int64).contiguous()
-            hits.append(h)
-            sc.body[p] = self.bodies[p].handle
-            sc.field[p] = self.fields[p].handle
-            sc.hit_index[p] = h.data_ptr()
-            sc.hit_count[p] = h.numel()
+            hits.append((h, cnt))
+            sc.body[k] = self.bodies[p].handle
+            sc.field[k] = self.fields[p].handle
+            sc.hit_index[k] = h.data_ptr()
+            sc.hit_count[k] = h.numel()
+            sc.hit_count_dev[k] = cnt.data_ptr() if cnt is not None else None
         sc.bg_field = self.bg.handle if self.bg is not None else None
         need = lib.mp_render_workspace_bytes(C.byref(sc), R)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if self._status is None:
+            self._status = torch.zeros(1, dtype=torch.int32, device=dev)
         out = L.RenderOut()
-        res = {
-            "rgb_values": torch.empty(R, 3, device=dev),
-            "fg_rgb_values": torch.empty(R, 3, device=dev),
-            "normal_values": torch.empty(R, 3, device=dev),
-            "acc_map": torch.empty(R, device=dev),
-            "acc_person_list": torch.empty(R, self.P, device=dev),
-        }
+        shapes = {"rgb_values": (R, 3), "fg_rgb_values": (R, 3), "normal_values": (R, 3), "acc_map": (R,),
+                  "acc_person_list": (R, Pn)}
+        if out_bufs is not None:
+            res = {k: out_bufs[k] for k in shapes}
+            for k, shp in shapes.items():
+                t = res[k]
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shp, k
+        else:
+            res = {k: torch.empty(*shp, device=dev) for k, shp in shapes.items()}
         for k, v in res.items():
             setattr(out, k, v.data_ptr())
+        out.status = self._status.data_ptr()
         dbg = {}
         if debug:
+            assert not dev_counts, "debug taps need host-side hit counts"
             n = self.n
-            dbg["trips"] = torch.zeros(self.P, dtype=torch.int32, device=dev)
+            dbg["trips"] = torch.zeros(Pn, dtype=torch.int32, device=dev)
             dbg["bg_T"] = torch.empty(R, device=dev)
             out.trips = dbg["trips"].data_ptr()
             out.bg_T = dbg["bg_T"].data_ptr()
-            for p in range(self.P):
-                Rp = hits[p].numel()
-                dbg[f"z_vals_{p}"] = torch.empty(Rp, n + 1, device=dev)
-                dbg[f"sdf_{p}"] = torch.empty(Rp, n, device=dev)
-                dbg[f"rgb_{p}"] = torch.empty(Rp, n, 3, device=dev)
-                dbg[f"normals_{p}"] = torch.empty(Rp, n, 3, device=dev)
-                out.z_vals[p] = dbg[f"z_vals_{p}"].data_ptr()
-                out.sdf[p] = dbg[f"sdf_{p}"].data_ptr()
-                out.rgb[p] = dbg[f"rgb_{p}"].data_ptr()
-                out.normals[p] = dbg[f"normals_{p}"].data_ptr()
+            for k in range(Pn):
+                Rp = hits[k][0].numel()
+                dbg[f"z_vals_{k}"] = torch.empty(Rp, n + 1, device=dev)
+                dbg[f"sdf_{k}"] = torch.empty(Rp, n, device=dev)
+                dbg[f"rgb_{k}"] = torch.empty(Rp, n, 3, device=dev)
+                dbg[f"normals_{k}"] = torch.empty(Rp, n, 3, device=dev)
+                out.z_vals[k] = dbg[f"z_vals_{k}"].data_ptr()
+                out.sdf[k] = dbg[f"sdf_{k}"].data_ptr()
+                out.rgb[k] = dbg[f"rgb_{k}"].data_ptr()
+                out.normals[k] = dbg[f"normals_{k}"].data_ptr()
         L.check(lib.mp_render_rays(C.byref(sc), uv.data_ptr(), pose.data_ptr(), K.data_ptr(), R, C.byref(out),
                                    self._ws.data_ptr(), self._ws.numel(), L.stream_ptr()), "mp_render_rays")
         self._keep = (uv, pose, K, hits)
+        if check or debug:
+            self.check_status()
         res.update(dbg)
         return res
+
+
+def ray_aabb_hits(cam_loc, ray_dirs, verts, inflate=1.2):
+    """Device-side culling against the x`inflate` axis-aligned box of `verts` [V,3] (multiply.py:208-214 uses trimesh's
+    oriented box): returns (ids [R] int64, count [1] int32), both on the device, the list already
+    finalised (empty -> ray 0, multiply.py:262-263).  No host synchronisation: feed the pair to ``Renderer.render``."""
+    lib = L.lib()
+    dev = cam_loc.device
+    cam = cam_loc.detach().contiguous().float()
+    d = ray_dirs.detach().contiguous().float()
+    v = verts.detach().reshape(-1, 3).contiguous().float()
+    R = cam.shape[0]
+    with torch.cuda.device(dev):
+        idx = torch.empty(R, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        box = torch.empty(8, dtype=torch.float64, device=dev)
+        L.check(lib.mp_ray_aabb_hits(cam.data_ptr(), d.data_ptr(), R, v.data_ptr(), v.shape[0], float(inflate),
+                                     idx.data_ptr(), cnt.data_ptr(), box.data_ptr(), L.stream_ptr()), "mp_ray_aabb_hits")
+    return idx, cnt
 
 
 def ray_box_hits(cam_loc, ray_dirs, center, half_extent, rot=None):

@@ -48,6 +48,11 @@ class Multiply(nn.Module):
         self.ray_sampler = ErrorBoundSampler(self.sdf_bounding_sphere, inverse_sphere_bg=True, **rs)
         self._renderer = None
         self._key = None
+        self.output_buffers = None      # optional dict of preallocated output tensors (parallel.PixelBuffer.views)
+        # the packed kernels are built for the shipped network shapes (confs/model/*.yaml:12,17-58): fail loudly otherwise
+        fe = _get(opt, "dim_frame_encoding")
+        if fe != 32:
+            raise NotImplementedError("dim_frame_encoding = %r: the background chain is packed for 32" % (fe,))
 
     # ---- packed device state ---------------------------------------------------------------
     @property
@@ -59,9 +64,12 @@ class Multiply(nn.Module):
                     persons=persons,
                     bg_implicit={k: v.detach() for k, v in self.bg_implicit_network.state_dict().items()},
                     bg_render={k: v.detach() for k, v in self.bg_rendering_network.state_dict().items()},
-                    frame_code=torch.zeros(1, 32), beta_param=float(self.density.beta.detach()))
+                    frame_code=torch.zeros(1, self.frame_latent_encoder.embedding_dim),
+                    beta_param=float(self.density.beta.detach()), beta_min=float(self.density.beta_min))
 
     def _ensure_renderer(self, device, persons=None):
+        """(Re)packs the weights when a parameter changed (``_version`` counters); the per-frame state (pose, cond,
+        frame code) goes through ``update_person`` / ``set_cond`` and never repacks."""
         key = (str(device), tuple(int(p._version) for p in self.parameters()))
         if self._renderer is None or self._key != key:
             if persons is None:
@@ -83,6 +91,25 @@ class Multiply(nn.Module):
         d["cond"] = cond if cond is not None else torch.zeros(1, 69)
         return d
 
+    def load_reference_checkpoint(self, state_dict, strict=True):
+        """Loads a reference checkpoint: a Lightning ``ckpt['state_dict']`` (keys prefixed ``model.``,
+        train.py:16-22 / multiply_model.py:81-92) or a bare ``Multiply.state_dict()``.  The reference registers
+        ``smpl_server_list`` / ``deformer_list`` as ModuleLists whose SMPL modules carry the body-model buffers
+        (body_models.py:152-249) and the sampler has none; those keys belong to the injected SMPL servers here and are
+        dropped, as are the training-only ``body_model_list`` / ``mesh_*`` entries.  Everything else must match
+        exactly when ``strict``."""
+        sd = {}
+        for k, v in state_dict.items():
+            if k.startswith("model."):
+                k = k[len("model."):]
+            elif "." in k and k.split(".")[0] in ("body_model_list", "loss", "sam_server"):
+                continue
+            if k.split(".")[0] in ("smpl_server_list", "deformer_list", "smpl_server", "deformer", "ray_sampler",
+                                   "mesh_v_cano_list", "mesh_f_cano_list", "mesh_face_vertices_list"):
+                continue
+            sd[k] = v
+        return self.load_state_dict(sd, strict=strict)
+
     # ---- operator surface the sampler / callers use (multiply.py:137-151) --------------------------
     def sdf_func_with_smpl_deformer(self, x, cond, smpl_tfs, smpl_verts, person_id):
         """multiply.py:137-151: canonicalise x against person ``person_id``'s posed SMPL (nearest vertex, inverse
@@ -101,23 +128,42 @@ class Multiply(nn.Module):
 
     # ---- Multiply.forward, eval branch -------------------------------------------------------
     def forward(self, input, id=-1, cond_zero_shit=False, canonical_pose=False):
+        """multiply.py:174-598, eval branch.  ``id``: render only that person (``person_list = [id]``, :244-247: its
+        samples alone are composited and ``acc_person_list`` is [R,1]); ``canonical_pose``: every SMPL server is
+        evaluated at zero translation and the canonical hip pose (:196-201) while the pose conditioning of the
+        networks still comes from ``smpl_pose`` (:270).  No host synchronisation happens on this path when the SMPL
+        servers live on the device (model.smpl.SMPLServer): SMPL forward, culling, sampling, MLPs and compositing
+        are all enqueued asynchronously."""
         if self.training:
             raise NotImplementedError("training-mode forward/backward is a 'next' row (SURVEY.md §8f-1); "
                                       "call .eval() — validation/test steps do (multiply_model.py:982,1624)")
-        if id != -1 or canonical_pose:
-            raise NotImplementedError("single-person (id) / canonical-pose rendering: next row")
         dev = input["uv"].device
         smpl_params, smpl_pose = input["smpl_params"], input["smpl_pose"]
         scale = smpl_params[:, :, 0]
         smpl_shape, smpl_trans = input["smpl_shape"], input["smpl_trans"]
         P = smpl_trans.shape[1]
+        if id != -1 and not (0 <= int(id) < P):
+            raise IndexError("person id %r out of range (num_person = %d)" % (id, P))
         persons = []
         for i in range(P):
-            out = self.smpl_server_list[i](scale[:, i], smpl_trans[:, i], smpl_pose[:, i], smpl_shape[:, i])
+            if canonical_pose:                                             # multiply.py:196-201
+                cpose = torch.zeros_like(smpl_pose[:, i])
+                cpose[0, 5] = np.pi / 6
+                cpose[0, 8] = -np.pi / 6
+                out = self.smpl_server_list[i](scale[:, i], torch.zeros_like(smpl_trans[:, i]), cpose, smpl_shape[:, i])
+            else:
+                out = self.smpl_server_list[i](scale[:, i], smpl_trans[:, i], smpl_pose[:, i], smpl_shape[:, i])
             cond_pose = smpl_pose[:, i, 3:] / np.pi                        # multiply.py:270
-            persons.append(self._person_dict(i, out, cond_pose))
-        r = self._ensure_renderer(dev, persons)
-        for i in range(P):
+            persons.append(dict(verts_p=out["smpl_verts"].reshape(-1, 3), tfs=out["smpl_tfs"].reshape(24, 4, 4),
+                                cond=cond_pose))
+        if self._renderer is None:
+            full = [self._person_dict(i, dict(smpl_verts=persons[i]["verts_p"], smpl_tfs=persons[i]["tfs"]),
+                                      persons[i]["cond"]) for i in range(P)]
+            r = self._ensure_renderer(dev, full)
+        else:
+            r = self._ensure_renderer(dev)
+        person_list = list(range(P)) if id == -1 else [int(id)]            # multiply.py:244-247
+        for i in person_list:
             r.update_person(i, persons[i])
         if "image_id" in input:
             frame = self.frame_latent_encoder(input["image_id"])          # multiply.py:407-410
@@ -129,20 +175,32 @@ class Multiply(nn.Module):
             r.bg.set_cond(frame.detach())
         hits = input.get("index_ray_box_list")
         if hits is None:
-            # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2, on the device
+            # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2 — box, test, ordered compaction and
+            # the empty-list rule all on the device; the count stays there
             dirs, cam = rend_util.get_camera_params(input["uv"], input["pose"], input["intrinsics"])
             dirs = dirs[0]
             cam = cam.expand(dirs.shape[0], 3).contiguous()
-            hits = []
-            for i in range(P):
-                v = persons[i]["verts_p"]
-                lo, hi = v.min(0)[0], v.max(0)[0]
-                hits.append(engine.ray_box_hits(cam, dirs, ((lo + hi) / 2).tolist(), ((hi - lo) / 2 * 1.2).tolist()))
+            hits = [engine.ray_aabb_hits(cam, dirs, persons[i]["verts_p"], 1.2) for i in person_list]
+        elif len(hits) == P and len(person_list) != P:
+            hits = [hits[i] for i in person_list]
         bg_saved = r.bg
         if frame is None:
             r.bg = None                                                    # white background, multiply.py:540-541
         try:
-            out = r.render(input, hits)
+            ob = self.output_buffers if (self.output_buffers is not None and id == -1) else None
+            out = r.render(input, hits, persons=person_list, out=ob)
         finally:
             r.bg = bg_saved
         return {k: out[k] for k in ("acc_map", "acc_person_list", "rgb_values", "fg_rgb_values", "normal_values")}
+
+    def query_oc(self, x, cond, person_id):
+        """multiply.py:169-172: canonical SDF of person ``person_id`` at x [..., 3] under pose conditioning
+        ``cond['smpl']`` [1,69] -> {'occ': [N,1]} (the mesh extractor's callback, lib/utils/mesh.py:78-132)."""
+        dev = x.device
+        r = self._ensure_renderer(dev)
+        f = r.fields[person_id]
+        c = cond["smpl"] if isinstance(cond, dict) else cond
+        with torch.cuda.device(dev):
+            f.set_cond(c.detach())
+            sdf, _ = f.implicit_forward(x.reshape(-1, 3), want_feat=False)
+        return {"occ": sdf.reshape(-1, 1)}

@@ -35,6 +35,29 @@ def unpack_pixels(rec, P):
             "acc_map": rec[:, 9], "acc_person_list": rec[:, 10:10 + P]}
 
 
+class PixelBuffer:
+    """The pixel record of a ray block as ONE flat device buffer [rgb R*3 | fg_rgb R*3 | normal R*3 | acc R |
+    acc_person R*P]; the renderer writes its outputs straight into the views (``Renderer.render(out=buf.views)``) and
+    a single all_gather_into_tensor of ``flat`` assembles the frame — no concatenation kernel in between."""
+
+    def __init__(self, R, P, device):
+        self.R, self.P = R, P
+        self.flat = torch.empty(R * (10 + P), device=device)
+        o = [0, 3 * R, 6 * R, 9 * R, 10 * R, (10 + P) * R]
+        f = self.flat
+        self.views = {"rgb_values": f[o[0]:o[1]].view(R, 3), "fg_rgb_values": f[o[1]:o[2]].view(R, 3),
+                      "normal_values": f[o[2]:o[3]].view(R, 3), "acc_map": f[o[3]:o[4]],
+                      "acc_person_list": f[o[4]:o[5]].view(R, P)}
+
+    @staticmethod
+    def frame(gathered, world, R, P):
+        """gathered [world, R*(10+P)] -> dict of full-frame tensors [world*R, ...] (copies: the blocks are strided)."""
+        g = gathered.view(world, -1)
+        cut = lambda a, b, w: g[:, a * R:b * R].reshape(world * R, w) if w > 1 else g[:, a * R:b * R].reshape(world * R)
+        return {"rgb_values": cut(0, 3, 3), "fg_rgb_values": cut(3, 6, 3), "normal_values": cut(6, 9, 3),
+                "acc_map": cut(9, 10, 1), "acc_person_list": g[:, 10 * R:(10 + P) * R].reshape(world * R, P)}
+
+
 def gather_pixels(out, total, group=None):
     """All-gather the per-rank pixel records into the full frame (every rank gets it).  Blocks may differ by
     one ray, so records are padded to the largest block for the collective."""
@@ -90,6 +113,11 @@ def exchange_plan(hit_lists, total_rays, world):
     return plan
 
 
+def _global_rank(group, r):
+    """P2POp peers are GLOBAL ranks; `r` is a rank of `group`."""
+    return r if group is None else dist.get_global_rank(group, r)
+
+
 def exchange_person_rows(rows, plan, width, rank, world, device, group=None):
     """rows: {p: [R_p, width] tensor} for the persons this rank owns.  Returns {p: [cnt_p, width]} for every person:
     the rows of this rank's ray block.  One batch of point-to-point transfers (the all-to-all by ray block)."""
@@ -104,11 +132,11 @@ def exchange_person_rows(rows, plan, width, rank, world, device, group=None):
             for b in range(world):
                 blo, bhi = plan[p][b]
                 if b != rank and bhi > blo:
-                    ops.append(dist.P2POp(dist.isend, rows[p][blo:bhi].contiguous(), b, group))
+                    ops.append(dist.P2POp(dist.isend, rows[p][blo:bhi].contiguous(), _global_rank(group, b), group))
         else:
             got[p] = torch.empty(hi - lo, width, device=device, dtype=torch.float32)
             if hi > lo:
-                ops.append(dist.P2POp(dist.irecv, got[p], own, group))
+                ops.append(dist.P2POp(dist.irecv, got[p], _global_rank(group, own), group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()

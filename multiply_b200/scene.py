@@ -343,11 +343,11 @@ def make_hit_lists(scene, inputs, all_hit=False):
     return out
 
 
-def make_smpl_model(seed=300):
+def make_smpl_model(seed=300, body_seed=100):
     """Synthetic stand-in for the licence-gated SMPL pkl: the arrays lib/smpl/body_models.py:SMPL registers
     (v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights), with SMPL's shapes."""
     rng = np.random.RandomState(seed)
-    verts_t, W = make_body(100)
+    verts_t, W = make_body(body_seed)
     V = verts_t.shape[0]
     shapedirs = 0.01 * rng.randn(V, 3, 10)
     posedirs = 0.004 * rng.randn(207, V * 3)
@@ -400,3 +400,91 @@ class SyntheticSMPLServer:
         dev = thetas.device
         return {"smpl_verts": f32(verts)[None].to(dev), "smpl_tfs": f32(tf)[None].to(dev),
                 "smpl_weights": self.weights.to(dev)}
+
+
+# ------------------------------------------------------------------------------------
+# drop-in scene: bodies produced by the DEVICE SMPL server (model.smpl.SMPLServer / mp_smpl_forward), so that
+# Multiply.forward(input_dict) and the resident-input Renderer see the same scene (bench.py, tests)
+# ------------------------------------------------------------------------------------
+
+MODEL_OPT = dict(
+    with_bkgd=True, num_training_frames=75, dim_frame_encoding=32,
+    implicit_network=dict(feature_vector_size=256, d_in=3, d_out=1, dims=[256] * 8, init="geometry", bias=0.6,
+                          skip_in=[4], weight_norm=True, embedder_mode="fourier", multires=6, cond="smpl"),
+    rendering_network=dict(feature_vector_size=256, mode="pose_no_view", d_in=14, d_out=3, dims=[256] * 4,
+                           weight_norm=True, multires_view=-1),
+    bg_implicit_network=dict(feature_vector_size=256, d_in=4, d_out=1, dims=[256] * 8, init="none", bias=0.0,
+                             skip_in=[4], weight_norm=False, embedder_mode="fourier", multires=10, cond="frame"),
+    bg_rendering_network=dict(feature_vector_size=256, mode="nerf_frame_encoding", d_in=3, d_out=3, dims=[128],
+                              weight_norm=False, multires_view=4),
+    density=dict(params_init={"beta": 0.1}, beta_min=0.0001),
+)
+
+
+def smpl_scene_inputs(P, frame_index=3, pose_std=0.2, scale=0.5):
+    """The SMPL entries of the reference's input dict for the synthetic P-person scene."""
+    smpl_pose = torch.zeros(1, P, 72)
+    smpl_trans = torch.zeros(1, P, 3)
+    for p in range(P):
+        rng = np.random.RandomState(200 + p)
+        theta = rng.normal(0, pose_std, size=(24, 3))
+        theta[0] = rng.normal(0, 0.1, size=3)
+        smpl_pose[0, p] = torch.from_numpy(theta.reshape(72).astype(np.float32))
+        smpl_trans[0, p] = torch.tensor([0.8 * (p - (P - 1) / 2.0), 0.15, 0.3 * p])
+    smpl_params = torch.zeros(1, P, 86)
+    smpl_params[:, :, 0] = scale
+    return dict(smpl_params=smpl_params, smpl_pose=smpl_pose, smpl_shape=torch.zeros(1, P, 10),
+                smpl_trans=smpl_trans, idx=torch.tensor([frame_index]))
+
+
+def smpl_scene_networks(P, S, seed):
+    """Networks / sampler config of the drop-in scene (everything but the bodies): returns (per-person net dicts, rest)."""
+    gen = torch.Generator().manual_seed(seed)
+    nets = [dict(implicit=init_implicit_fg(gen), render=init_render_fg(gen)) for _ in range(P)]
+    rest = dict(cfg=make_cfg(S), bg_implicit=init_implicit_bg(gen), bg_render=init_render_bg(gen),
+                frame_code=torch.randn(1, 32, generator=torch.Generator().manual_seed(7)), beta_param=0.1)
+    return nets, rest
+
+
+def make_smpl_scene(P=2, S=64, seed=42, device="cuda", frame_index=3, pose_std=0.2, scale=0.5):
+    """Returns (scene, model, smpl_inputs): `scene` is a make_scene-style dict (CPU tensors) whose persons are the
+    outputs of the device SMPL servers for `smpl_inputs` (smpl_params / smpl_pose / smpl_shape / smpl_trans / idx, the
+    reference's input-dict entries); `model` is the mirror ``Multiply`` (eval, on `device`) holding the
+    same weights and servers."""
+    from .model.smpl import SMPLServer
+    from .model.multiply import Multiply
+    servers = [SMPLServer(model=make_smpl_model(300 + p, body_seed=100 + p), device=device) for p in range(P)]
+    smpl_inputs = smpl_scene_inputs(P, frame_index, pose_std, scale)
+    smpl_params, smpl_pose, smpl_trans = smpl_inputs["smpl_params"], smpl_inputs["smpl_pose"], smpl_inputs["smpl_trans"]
+    nets, rest = smpl_scene_networks(P, S, seed)
+    persons = []
+    for p in range(P):
+        o = servers[p](smpl_params[:, p, 0], smpl_trans[:, p], smpl_pose[:, p], torch.zeros(1, 10))
+        torch.cuda.synchronize()
+        servers[p].scale = scale
+        persons.append(dict(verts_c=servers[p].verts_c[0].cpu(), weights=servers[p].weights[0].cpu(),
+                            verts_p=o["smpl_verts"][0].cpu(), tfs=o["smpl_tfs"][0].cpu(),
+                            smpl_pose=smpl_pose[:, p].clone(), cond=smpl_pose[:, p, 3:] / math.pi, scale=scale,
+                            implicit=nets[p]["implicit"], render=nets[p]["render"]))
+    scene = dict(rest, persons=persons)
+    opt = dict(MODEL_OPT, ray_sampler=dict({k: v for k, v in scene["cfg"].items()
+                                            if k in ("near", "N_samples", "N_samples_eval", "N_samples_extra", "eps",
+                                                     "beta_iters", "max_total_iters", "add_tiny")},
+                                           N_samples_inverse_sphere=32))
+    model = Multiply(opt, smpl_server_list=servers)
+    sd = {}
+    for p, person in enumerate(persons):
+        for k, v in person["implicit"].items():
+            sd[f"foreground_implicit_network_list.{p}.{k}"] = v
+        for k, v in person["render"].items():
+            sd[f"foreground_rendering_network_list.{p}.{k}"] = v
+    for k, v in scene["bg_implicit"].items():
+        sd["bg_implicit_network." + k] = v
+    for k, v in scene["bg_render"].items():
+        sd["bg_rendering_network." + k] = v
+    sd["density.beta"] = torch.tensor(scene["beta_param"])
+    fw = torch.zeros(75, 32)
+    fw[frame_index] = scene["frame_code"][0]
+    sd["frame_latent_encoder.weight"] = fw
+    model.load_state_dict(sd, strict=True)
+    return scene, model.to(device).eval(), smpl_inputs

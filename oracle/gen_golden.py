@@ -247,6 +247,46 @@ def main():
     # ---- sampler + full forward -----------------------------------------------------
     for case in FORWARD_CASES:
         forward_case(ref, *case)
+    rays_case(ref)
+    grid_case(ref)
+
+
+def grid_case(ref):
+    """Multiply.query_oc (multiply.py:169-172) on the dense lattice of generate_mesh (lib/utils/mesh.py:78-105; the
+    point mapping of :92-95 is restated here because generate_mesh itself needs the compiled MISE extension)."""
+    sc = S.make_scene(P=2, S=64, seed=42)
+    m = build_ref_model(ref, sc)
+    p1 = sc["persons"][1]
+    res = 12
+    center, extent, scale = port.mesh_bounds(p1["verts_c"])
+    idx = np.stack(np.meshgrid(np.arange(res + 1), np.arange(res + 1), np.arange(res + 1), indexing="ij"), -1).reshape(-1, 3)
+    pts = idx.astype(np.float32)
+    pts = (pts / res - 0.5) * scale
+    pts = pts * extent + center
+    with torch.no_grad():
+        occ = ref.multiply.Multiply.query_oc(m, torch.tensor(pts).float(), {"smpl": p1["cond"]}, 1)["occ"]
+    save("sdf_grid", res=np.array(res), center=center, extent=np.array(extent), points=pts, occ=occ[:, 0])
+
+
+def rays_case(ref):
+    """rend_util.get_camera_params (:45-72, quaternion and matrix poses are both 4x4 here) with a skewed, off-centre
+    intrinsic matrix and a rotated camera, and get_sphere_intersections (:131-147) at r = 3 (multiply.py:85)."""
+    g = torch.Generator().manual_seed(77)
+    R = 300
+    uv = torch.rand(1, R, 2, generator=g) * 512.0
+    K = torch.eye(4)[None].clone()
+    K[0, 0, 0], K[0, 1, 1], K[0, 0, 2], K[0, 1, 2], K[0, 0, 1] = 880.0, 910.0, 250.0, 262.0, 3.5
+    ax = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
+    ang = 0.4
+    Kx = torch.tensor([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    Rm = torch.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * (Kx @ Kx)
+    pose = torch.eye(4)[None].clone()
+    pose[0, :3, :3] = Rm
+    pose[0, :3, 3] = torch.tensor([0.3, -0.2, 2.2])
+    dirs, cam = ref.rend_util.get_camera_params(uv, pose, K)
+    cam_r = cam.unsqueeze(1).repeat(1, R, 1).reshape(-1, 3)
+    nf = ref.rend_util.get_sphere_intersections(cam_r, dirs.reshape(-1, 3), r=3.0)
+    save("rays", uv=uv, pose=pose, intrinsics=K, ray_dirs=dirs, cam_loc=cam, near_far=nf)
 
 
 # (name, persons, N_samples, rays, ray region, scene seed)
@@ -282,5 +322,9 @@ if __name__ == "__main__":
         for case in FORWARD_CASES:
             if case[0] in sys.argv[2:]:
                 forward_case(_ref, *case)
+        if "rays" in sys.argv[2:]:
+            rays_case(_ref)
+        if "sdf_grid" in sys.argv[2:]:
+            grid_case(_ref)
     else:
         main()

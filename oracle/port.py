@@ -530,6 +530,34 @@ def get_rbg_value(pnts_c, person, cfg, chunk=32768):
 
 
 # --------------------------------------------------------------------------------------
+# canonical SDF grid queries (multiply.py:169-172, lib/utils/mesh.py:78-105)
+# --------------------------------------------------------------------------------------
+
+
+def mesh_bounds(verts, scale=1.1):
+    """generate_mesh, lib/utils/mesh.py:80-86: centre / longest side of the tight vertex box, padding factor."""
+    v = verts.detach().cpu().numpy().reshape(-1, 3)
+    bbox = np.stack([v.min(axis=0), v.max(axis=0)], axis=0)
+    return (bbox[0] + bbox[1]) * 0.5, (bbox[1] - bbox[0]).max(), scale
+
+
+def query_oc(x, person, cfg):
+    """Multiply.query_oc, multiply.py:169-172: canonical SDF at x [N,3] -> [N,1]."""
+    with torch.no_grad():
+        return implicit_forward(person["implicit"], x.reshape(-1, 3), person["cond"], cfg["multires"])[:, :1]
+
+
+def sdf_grid(person, cfg, verts, res, scale=1.1):
+    """The dense (res+1)^3 lattice of generate_mesh (:92-95 point mapping, numpy fp32) through query_oc."""
+    center, extent, scale = mesh_bounds(verts, scale)
+    idx = np.stack(np.meshgrid(np.arange(res + 1), np.arange(res + 1), np.arange(res + 1), indexing="ij"), -1).reshape(-1, 3)
+    pts = idx.astype(np.float32)
+    pts = (pts / res - 0.5) * scale
+    pts = pts * extent + center
+    return query_oc(torch.tensor(pts).float(), person, cfg)[:, 0].reshape(res + 1, res + 1, res + 1), pts
+
+
+# --------------------------------------------------------------------------------------
 # background (multiply.py:514-539, 682-726)
 # --------------------------------------------------------------------------------------
 

@@ -49,17 +49,7 @@ def _build(sc):
     return m.cuda().eval()
 
 
-def test_multiply_forward_drop_in():
-    """Multiply.forward(input) with the reference's input dict == oracle."""
-    from multiply_b200 import engine
-    from oracle import port
-    engine.set_engine("tc")
-    sc = S.make_scene(P=2, S=16, seed=42)
-    inp = S.make_rays(sc, 96, seed=11, region="boxes")
-    hits = S.make_hit_lists(sc, inp)
-    ref = port.multiply_forward(sc, inp, hits)
-    m = _build(sc)
-    P = 2
+def _drop_in_inputs(sc, inp, P, with_hits=None):
     transl = torch.tensor([[0.8 * (p - (P - 1) / 2.0), 0.15, 0.3 * p] for p in range(P)])[None]
     smpl_pose = torch.stack([sc["persons"][p]["smpl_pose"][0] for p in range(P)])[None]
     smpl_params = torch.zeros(1, P, 86)
@@ -67,11 +57,119 @@ def test_multiply_forward_drop_in():
     inputs = dict(uv=inp["uv"].cuda(), pose=inp["pose"].cuda(), intrinsics=inp["intrinsics"].cuda(),
                   smpl_params=smpl_params.cuda(), smpl_pose=smpl_pose.cuda(), smpl_shape=torch.zeros(1, P, 10).cuda(),
                   smpl_trans=transl.cuda(), idx=torch.tensor([3]).cuda())
-    out = m(inputs)
+    if with_hits is not None:
+        inputs["index_ray_box_list"] = with_hits
+    return inputs
+
+
+@pytest.mark.parametrize("pid", [-1, 0, 1])
+@pytest.mark.parametrize("device_culling", [False, True])
+def test_multiply_forward_drop_in(pid, device_culling):
+    """Multiply.forward(input, id) with the reference's input dict == oracle.  id = -1 renders both
+    persons, id = p only person p (multiply.py:244-247: person_list = [id], acc_person_list is [R,1]); with
+    device_culling the hit lists are not passed in but computed on the GPU (box, slab test, compaction, empty-list
+    rule) with the count left on the device."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 96, seed=11, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    plist = [0, 1] if pid == -1 else [pid]
+    sub = dict(sc, persons=[sc["persons"][p] for p in plist])
+    ref = port.multiply_forward(sub, inp, [hits[p] for p in plist])
+    m = _build(sc)
+    inputs = _drop_in_inputs(sc, inp, 2, None if device_culling else [h.cuda() for h in hits])
+    out = m(inputs, id=pid)
     torch.cuda.synchronize()
     assert set(out) == {"acc_map", "acc_person_list", "rgb_values", "fg_rgb_values", "normal_values"}
+    assert out["acc_person_list"].shape == (96, len(plist))
     for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
         assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4, k
+    # a second call (cached renderer, new pose upload) gives the same pixels
+    out2 = m(inputs, id=pid)
+    torch.cuda.synchronize()
+    assert torch.equal(out2["rgb_values"], out["rgb_values"])
+
+
+def test_multiply_forward_canonical_pose():
+    """canonical_pose=True (multiply.py:196-201): bodies at zero translation in the canonical hip pose, the pose
+    conditioning of the networks still from smpl_pose (:270)."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    m = _build(sc)
+    P = 2
+    cpose = torch.zeros(1, 72)
+    cpose[0, 5], cpose[0, 8] = math.pi / 6, -math.pi / 6
+    persons = []
+    for p in range(P):
+        o = S.SyntheticSMPLServer(p, P)(torch.tensor([0.5]), torch.zeros(1, 3), cpose, torch.zeros(1, 10))
+        persons.append(dict(sc["persons"][p], verts_p=o["smpl_verts"][0], tfs=o["smpl_tfs"][0]))
+    csc = dict(sc, persons=persons)
+    inp = S.make_rays(csc, 80, seed=13, region="boxes")
+    hits = S.make_hit_lists(csc, inp)
+    assert sum(h.numel() for h in hits) > 40
+    ref = port.multiply_forward(csc, inp, hits)
+    out = m(_drop_in_inputs(sc, inp, P, [h.cuda() for h in hits]), canonical_pose=True)
+    torch.cuda.synchronize()
+    for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4, k
+
+
+def test_device_culling_matches_host():
+    """mp_ray_aabb_hits (box from the posed vertices on the device, fp64 slab test, ordered compaction, empty -> ray 0)
+    against the host slab test of scene.make_hit_lists on 5000 rays; count stays on the device."""
+    from multiply_b200 import engine
+    from multiply_b200.model import rend_util
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 5000, seed=3, region="image")
+    dirs, cam = rend_util.get_camera_params_host(inp["uv"], inp["pose"], inp["intrinsics"])
+    ref = S.make_hit_lists(sc, inp)
+    for p, person in enumerate(sc["persons"]):
+        idx, cnt = engine.ray_aabb_hits(cam.cuda(), dirs.cuda(), person["verts_p"].cuda(), 1.2)
+        n = int(cnt.item())
+        assert torch.equal(idx[:n].cpu(), ref[p])
+    # rays in an image corner miss the box: the list becomes [0] on the device (multiply.py:262-263)
+    uv = torch.rand(1, 33, 2, generator=torch.Generator().manual_seed(4)) * 6.0
+    K, pose = S.make_camera()
+    dirs, cam = rend_util.get_camera_params_host(uv, pose, K)
+    idx, cnt = engine.ray_aabb_hits(cam.cuda(), dirs.cuda(), sc["persons"][0]["verts_p"].cuda(), 1.2)
+    assert int(cnt.item()) == 1 and int(idx[0].item()) == 0
+
+
+def test_query_oc_and_dense_grid(golden_dir):
+    """Multiply.query_oc (multiply.py:169-172) through the mirror, batch by batch as generate_mesh calls it
+    (lib/utils/mesh.py:97-100), and utils.mesh.dense_sdf_grid in one call: both equal the reference's values."""
+    import os
+    from multiply_b200 import engine
+    from multiply_b200.utils import mesh
+    engine.set_engine("tc")
+    g = np.load(os.path.join(golden_dir, "sdf_grid.npz"))
+    sc = S.make_scene(P=2, S=64, seed=42)
+    m = _build(sc)
+    p1 = sc["persons"][1]
+    cond = {"smpl": p1["cond"].cuda()}
+    pts = torch.from_numpy(g["points"]).cuda()
+    occ = torch.cat([m.query_oc(b, cond, 1)["occ"] for b in torch.split(pts, 500, dim=0)])
+    assert occ.shape == (pts.shape[0], 1)
+    assert float(np.abs(occ[:, 0].cpu().numpy() - g["occ"]).max()) < 5e-5
+    dense = mesh.dense_sdf_grid(m, 1, cond, p1["verts_c"], res=int(g["res"]))
+    assert torch.equal(dense.reshape(-1), occ[:, 0])
+
+
+def test_load_reference_checkpoint_keys():
+    """A Lightning checkpoint of the reference (keys 'model.*', plus smpl_server_list / deformer_list buffers and
+    MultiplyModel's body_model_list, train.py:16-22) loads through load_reference_checkpoint with strict=True."""
+    sc = S.make_scene(P=2, S=16, seed=42)
+    m = _build(sc)
+    sd = {"model." + k: v for k, v in m.state_dict().items()}
+    sd["model.smpl_server_list.0.smpl.v_template"] = torch.zeros(6890, 3)
+    sd["model.deformer_list.1.smpl.smpl.lbs_weights"] = torch.zeros(6890, 24)
+    sd["body_model_list.0.betas.weight"] = torch.zeros(1, 10)
+    res = m.load_reference_checkpoint(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
 
 
 def test_operator_mirrors():

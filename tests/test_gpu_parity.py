@@ -66,6 +66,78 @@ def test_implicit_grad(golden_dir, field0, eng):
     assert _maxabs(grad.cpu().numpy(), g["grad"]) < 2 * TOL_NET[eng]
 
 
+def test_camera_rays_and_sphere(golden_dir):
+    """a1 / a2 at the operator level: mp_camera_rays and mp_sphere_intersections against what the reference's own
+    rend_util.get_camera_params / get_sphere_intersections computed (skewed off-centre intrinsics, rotated camera)."""
+    from multiply_b200.model import rend_util
+    g = _g(golden_dir, "rays")
+    dirs, cam = rend_util.get_camera_params(torch.from_numpy(g["uv"]).cuda(), torch.from_numpy(g["pose"]).cuda(),
+                                            torch.from_numpy(g["intrinsics"]).cuda())
+    assert dirs.shape == (1, 300, 3) and cam.shape == (1, 3)
+    assert _maxabs(dirs.cpu().numpy(), g["ray_dirs"]) < 2e-7
+    assert _maxabs(cam.cpu().numpy(), g["cam_loc"]) == 0.0
+    cam_r = cam.expand(300, 3).contiguous()
+    nf = rend_util.get_sphere_intersections(cam_r, torch.from_numpy(g["ray_dirs"][0]).cuda(), r=3.0)
+    assert _maxabs(nf.cpu().numpy(), g["near_far"]) < 2e-6
+    # a camera outside the sphere: the reference exits (rend_util.py:140-142), the mirror raises
+    with pytest.raises(RuntimeError):
+        rend_util.get_sphere_intersections(cam_r * 10.0, torch.from_numpy(g["ray_dirs"][0]).cuda(), r=3.0)
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+def test_background_nets(golden_dir, scene64, eng):
+    """a12 at the operator level: bg ImplicitNet (d_in 4, multires 10, frame cond) + bg RenderingNet
+    ('nerf_frame_encoding') through mp_bg_nets_forward against the reference modules' outputs."""
+    from multiply_b200 import engine
+    engine.set_engine(eng)
+    g = _g(golden_dir, "bg_nets")
+    f = engine.Field(scene64["bg_implicit"], scene64["bg_render"], background=True)
+    f.set_cond(scene64["frame_code"])
+    sdf, rgb = f.bg_forward(torch.from_numpy(g["x"]), torch.from_numpy(g["view"]))
+    torch.cuda.synchronize()
+    assert _maxabs(sdf.cpu().numpy(), g["out"][:, 0]) < TOL_NET[eng]
+    assert _maxabs(rgb.cpu().numpy(), g["rgb"]) < TOL_NET[eng]
+    sdf2, feat = f.implicit_forward(torch.from_numpy(g["x"]))
+    assert _maxabs(sdf2.cpu().numpy(), g["out"][:, 0]) < TOL_NET[eng]
+    assert _maxabs(feat.cpu().numpy(), g["out"][:, 1:]) < TOL_NET[eng]
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+def test_sdf_grid(golden_dir, scene64, eng):
+    """f3: canonical SDF on the dense lattice of generate_mesh (mp_sdf_grid: points generated on the device, streamed
+    through the sdf-only program) against the reference's Multiply.query_oc on the same lattice; the lattice points
+    themselves are bit-equal to numpy's (checked through a second query at the golden points)."""
+    from multiply_b200 import engine
+    engine.set_engine(eng)
+    g = _g(golden_dir, "sdf_grid")
+    p1 = scene64["persons"][1]
+    f = engine.Field(p1["implicit"], p1["render"])
+    f.set_cond(p1["cond"])
+    res = int(g["res"])
+    vals = f.sdf_grid(g["center"], float(g["extent"]), res)
+    torch.cuda.synchronize()
+    assert vals.shape == (res + 1,) * 3
+    assert _maxabs(vals.cpu().numpy().reshape(-1), g["occ"]) < TOL_NET[eng]
+    direct, _ = f.implicit_forward(torch.from_numpy(g["points"]), want_feat=False)
+    assert torch.equal(direct, vals.reshape(-1))           # same points bit for bit -> same SDF bit for bit
+
+
+def test_sphere_status_flag():
+    """mp_render_rays reports a camera outside the bounding sphere through mp_render_out_t.status; the Renderer raises
+    where the reference exits."""
+    from multiply_b200 import engine
+    engine.set_engine("tc")
+    sc = S.make_scene(P=1, S=16, seed=42)
+    inp = S.make_rays(sc, 16, seed=2, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    r = engine.Renderer(sc)
+    r.render(inp, hits, check=True)
+    far = dict(inp, pose=inp["pose"].clone())
+    far["pose"][0, :3, 3] *= 4.0
+    with pytest.raises(RuntimeError, match="BOUNDING SPHERE"):
+        r.render(far, hits, check=True)
+
+
 def test_render_forward(golden_dir, field0):
     g = _g(golden_dir, "render_fg")
     rgb = field0.render_forward(torch.from_numpy(g["x"]), torch.from_numpy(g["normals"]), torch.from_numpy(g["feat"]))
@@ -177,6 +249,30 @@ def test_forward_vs_oracle(eng):
     assert list(o["trips"].cpu().numpy()) == list(st["trips"])
     for k in ("rgb_values", "fg_rgb_values", "normal_values", "acc_map", "acc_person_list"):
         assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < 1e-4, k
+    for p in range(2):
+        assert _sdf_where_z_agrees(o, ref, p) < 1e-4
+
+
+def test_forward_config1_scale():
+    """BASELINE configs[1] sampler sizes (S/E/X = 128/256/64, n = 193 main-pass samples, 2 persons) on 512 rays of
+    the benchmark batch against the CPU oracle: trips equal, every output of Multiply.forward within 1e-4, per-sample
+    SDF within 1e-4 wherever both sides sampled the same depth."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    sc = S.make_scene(P=2, S=128, seed=42)
+    full = S.make_rays(sc, 4096, seed=1234, region="boxes")
+    inp = dict(uv=full["uv"][:, :512].contiguous(), pose=full["pose"], intrinsics=full["intrinsics"])
+    hits = S.make_hit_lists(sc, inp)
+    st = {}
+    ref = port.multiply_forward(sc, inp, hits, stats=st, return_samples=True)
+    o = engine.Renderer(sc).render(inp, hits, debug=True)
+    torch.cuda.synchronize()
+    assert list(o["trips"].cpu().numpy()) == list(st["trips"])
+    for k in ("rgb_values", "fg_rgb_values", "acc_map", "acc_person_list"):
+        assert _maxabs(o[k].cpu().numpy(), ref[k].numpy()) < 1e-4, k
+    assert _maxabs(o["normal_values"].cpu().numpy(), ref["normal_values"].numpy()) < TOL_NORMAL["tc"]
     for p in range(2):
         assert _sdf_where_z_agrees(o, ref, p) < 1e-4
 

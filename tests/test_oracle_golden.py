@@ -105,3 +105,25 @@ def test_smpl_lbs(golden_dir):
     verts, A = port.lbs(torch.from_numpy(g["betas"])[0], torch.from_numpy(g["pose"])[0], sm)
     assert np.abs(verts.numpy() - g["verts"]).max() < 2e-6
     assert np.abs(A.numpy() - g["A"]).max() < 2e-6
+
+
+def test_rays(golden_dir):
+    """port.get_camera_params / get_sphere_intersections against the reference's rend_util (skewed intrinsics,
+    rotated camera)."""
+    g = _g(golden_dir, "rays")
+    dirs, cam = port.get_camera_params(torch.from_numpy(g["uv"]), torch.from_numpy(g["pose"]),
+                                       torch.from_numpy(g["intrinsics"]))
+    assert np.abs(dirs.numpy() - g["ray_dirs"]).max() < 1e-7
+    assert np.abs(cam.numpy() - g["cam_loc"]).max() == 0.0
+    cam_r = cam.unsqueeze(1).repeat(1, 300, 1).reshape(-1, 3)
+    nf = port.get_sphere_intersections(cam_r, dirs.reshape(-1, 3), r=3.0)
+    assert np.abs(nf.numpy() - g["near_far"]).max() < 1e-6
+
+
+def test_sdf_grid(golden_dir, scene64):
+    """port.sdf_grid (generate_mesh lattice + query_oc) against the reference's Multiply.query_oc."""
+    g = _g(golden_dir, "sdf_grid")
+    p1 = scene64["persons"][1]
+    vals, pts = port.sdf_grid(p1, dict(scene64["cfg"], multires=6), p1["verts_c"], int(g["res"]))
+    assert np.array_equal(pts, g["points"])
+    assert np.abs(vals.numpy().reshape(-1) - g["occ"]).max() < 2e-6
