@@ -93,6 +93,12 @@ int mp_field_set_cond(mp_net_t* f, const float* cond /*[cond_dim]*/, void* strea
 /* engine selection: 0 = fp32 SIMT (validation engine), 1 = tcgen05 split-fp16 tensor-core engine */
 int mp_set_engine(int engine);
 int mp_get_engine(void);
+/* Precision mode of the tcgen05 engine: which split-precision product terms each MLP layer issues (fp16 hi/lo operand
+ * pairs, fp32 accumulation).  0 = parity (default): A_hi.W_hi + A_lo.W_hi + A_hi.W_lo everywhere (RGB / SDF within 1e-4 of
+ * the fp32 reference); 1 = the colour layers issue A_hi.W_hi only (SDF / normals unchanged, RGB ~2e-5); 2 = throughput:
+ * every layer single-term, i.e. plain fp16 operands — outside the 1e-4 gate, reported separately. */
+int mp_set_precision(int mode);
+int mp_get_precision(void);
 /* mp_render_rays schedule: 1 (default) = persons and background on their own streams, joined before the compositor;
  * 0 = everything on the caller's stream (used for per-kernel timing).  Environment override: MP_RENDER_STREAMS. */
 int mp_set_streams(int on);

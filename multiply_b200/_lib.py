@@ -81,6 +81,8 @@ SIGNATURES = {
     "mp_field_set_cond": (_I, [_VP, _VP, _VP]),
     "mp_set_engine": (_I, [_I]),
     "mp_get_engine": (_I, []),
+    "mp_set_precision": (_I, [_I]),
+    "mp_get_precision": (_I, []),
     "mp_profile_enable": (_I, [_I]),
     "mp_set_streams": (_I, [_I]),
     "mp_tc_trace_read": (_I, [C.POINTER(C.c_ulonglong), _I]),

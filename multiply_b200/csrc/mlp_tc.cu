@@ -87,7 +87,9 @@ struct TcIO {
   float* nrm_out;        // [slots,3]
   float* grad_out;       // [cap,3] dense or nullptr
   float* feat_out;       // [cap,256] dense or nullptr
-  int knobs;             // diagnostics (MP_TC_KNOBS bit mask): bit 1 = record the cycle stamps of mp_tc_trace_read
+  int knobs;             // diagnostics (MP_TC_KNOBS bit mask): bit 1 = record the cycle stamps of mp_tc_trace_read,
+                         // bit 2 = keep the dead scratch lines (no discard.global.L2)
+  float rz;              // relative truncation loss of ONE tensor-core accumulation (see kRzPerMma)
   char* scratch;         // per-CTA scratch
   size_t scratch_per_cta;
 };
@@ -577,7 +579,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
       float nrm[3] = {0.f, 0.f, 0.f};
       for (int s = 0; s < P.nsteps; ++s) {
         const TcStep st = P.step[s];
-        const float isc = P.inv_scale[st.sc];
+        // 2^-s of the weight scaling, times the compensation of the accumulator's round-toward-zero (kRzPerMma)
+        const float isc = P.inv_scale[st.sc] * fmaf(io.rz, (float)(4 * st.nk * (st.terms == 1 ? 1 : 3)), 1.f);
         // reverse-sweep steps: start fetching sigma' of the first chunk before blocking on the accumulator
         float4 s4[G4];
         const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
               *reinterpret_cast<uint4*>(A + o) = fh[u];
               *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
-              if ((lane & 7) == 0) {
+              if ((lane & 7) == 0 && !(io.knobs & 4)) {
                 discard_line(&fsc[(size_t)chunk * 128 + row], fh[u].x);
                 discard_line(&fsc[(size_t)(32 + chunk) * 128 + row], fl[u].x);
               }
@@ -800,7 +803,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 v[4 * g4 + 3] *= isc * s4[g4].w;
               }
             }
-            if (need_sig && (lane & 7) == 0) {   // this chunk's sigma' lines are dead: drop them from L2 without write-back
+            if (need_sig && (lane & 7) == 0 && !(io.knobs & 4)) {   // this chunk's sigma' lines are dead: drop them from L2 without write-back
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4)
                 discard_line(&sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row], v[4 * g4]);
@@ -999,7 +1002,7 @@ struct TcBlob {
   bool has_full;
 };
 
-__global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restrict__ out, float rz_comp) {
+__global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restrict__ out) {
   __shared__ float s[256];
   float m = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
@@ -1016,7 +1019,7 @@ __global__ void absmax_kernel(const float* __restrict__ W, int n, float* __restr
     if (mx > 0.f) frexpf(mx, &ex);       // mx = f * 2^ex, f in [0.5,1)
     float sc = ldexpf(1.f, 14 - ex);
     out[0] = sc;
-    out[1] = (1.f / sc) * (1.f + rz_comp);
+    out[1] = 1.f / sc;
   }
 }
 
@@ -1118,12 +1121,7 @@ static int pack_layer(PackCtx& c, TcStep& stp, const float* W, int ld, int trans
   stp.sc = step;
   stp.terms = 3;
   if (c.rc) return first;
-  static float rz_comp = -1.f;
-  if (rz_comp < 0.f) {
-    const char* e = getenv("MP_TC_RZ_COMP");      // experiment knob: relative compensation of the accumulator truncation
-    rz_comp = e ? (float)atof(e) : 0.f;
-  }
-  absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step, rz_comp);
+  absmax_kernel<<<1, 256, 0, c.st>>>(W, total_elems, c.scales + 2 * step);
   g_launches++;
   for (int kc = 0; kc < nk; ++kc) {
     uint8_t* hi = c.blob + (size_t)c.nslots * kSlotBytes;
@@ -1373,7 +1371,40 @@ int prof_read(double* ms, long long* launches, double* points, int reset) {
   return 0;
 }
 
-static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cudaStream_t st, int kind) {
+// Precision mode of the tcgen05 engine (mp_set_precision): which of the three split-precision product terms each layer
+// step issues.  The weight blob always holds the hi and lo slots; a single-term step just skips the lo slots.
+//   0  parity (default): every step A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  -- RGB / SDF within 1e-4 of the fp32 reference
+//   1  colour layers single-term (A_hi.W_hi): SDF / normals unchanged, RGB error ~2e-5 (still inside the gate)
+//   2  throughput: every step single-term, i.e. plain fp16 operands with fp32 accumulation -- misses the 1e-4 gate
+//      (SDF ~3e-4, normals ~1e-3; measured values in DESIGN.md) and is reported separately by bench.py
+std::atomic<int> g_precision{0};
+
+// The tensor core adds each MMA's products into the fp32 accumulator with round-toward-zero: every one of the
+// n = 4 nk terms accumulations of a layer step (K = 16 per tcgen05.mma) drops on average half an ulp of the running sum,
+// always toward zero.  Unlike round-to-nearest noise this loss is coherent -- every pre-activation shrinks by the same
+// relative amount, layer after layer -- and it is what kept the engine's SDF at 4e-6 and its gradients at 6e-6 from
+// the fp64 value of the same weights while the fp32 SIMT engine sits at 3e-7.  First-order model: a running sum that
+// grows linearly to its final value z loses  sum_i ulp(z i/n)/2 ~= (n/2) * E[ulp(z)/|z|]/2 * |z|, with
+// E[ulp/|z|] = 2^-23 / (2 ln 2) for a log-uniform mantissa: 2.15e-8 |z| per accumulation, 1.03e-6 |z| for the 48
+// accumulations of a 256-wide three-term layer.  The epilogue multiplies the accumulator by (1 + n * kRzPerMma), which
+// is free (it is folded into the 2^-s rescale).  The constant is the model's 2.15e-8 calibrated by one factor measured on
+// the device (scripts/gpu_normal_diag.py, 4096 points around the surface and 4096 near the canonical origin, against
+// the fp64 evaluation of the same weights; MP_TC_RZ_SCALE sweeps it):
+//   factor   SDF L-inf   d sdf/dx L-inf (mean)    rendered normals, 48-ray sample of the benchmark batch
+//   0        3.7e-6      6.0e-6 (4.0e-6)          4.8e-4   (one sample at |grad| ~ 1e-4 off by 0.07)
+//   0.8      5.8e-7      1.3e-6 (4.3e-7)          3.0e-6   <- kRzPerMma
+//   1.0      1.2e-6      2.1e-6 (1.1e-6)          3.7e-6
+//   1.2      1.6e-6      2.8e-6 (1.7e-6)          6.9e-6
+// (fp32 SIMT engine: 3.1e-7 / 7.1e-7 (1.9e-7) / 2.9e-6.)
+constexpr float kRzPerMma = 1.72e-8f;
+
+static int tc_launch(const TcProgram& P0, TcIO io, void* ws, size_t ws_bytes, cudaStream_t st, int kind) {
+  TcProgram P = P0;
+  {
+    const int mode = g_precision.load();
+    for (int s = 0; s < P.nsteps; ++s)
+      P.step[s].terms = (mode == 2 || (mode == 1 && P.step[s].epi == EPI_RELU)) ? 1 : 3;
+  }
   int grid = sm_count();
   {
     static int grid_override = -1;
@@ -1392,11 +1423,15 @@ static int tc_launch(const TcProgram& P, TcIO io, void* ws, size_t ws_bytes, cud
   io.scratch_per_cta = kScratchPerCta;
   {
     static int knobs = -1;
+    static float rz_scale = 1.f;
     if (knobs < 0) {
+      const char* er = getenv("MP_TC_RZ_SCALE");      // experiment knob: multiplies kRzPerMma (0 switches it off)
+      rz_scale = er ? (float)atof(er) : 1.f;
       const char* ek = getenv("MP_TC_KNOBS");
       knobs = ek ? atoi(ek) : 0;
     }
     io.knobs = knobs;
+    io.rz = kRzPerMma * rz_scale;
   }
   {
     // the > 48 KB dynamic shared memory opt-in is per device

@@ -8,6 +8,7 @@
 namespace mp {
 
 std::atomic<int> g_engine{1};
+extern std::atomic<int> g_precision;      // mlp_tc.cu
 
 // mlp_tc.cu
 int tc_sdf_list(const Field& f, const float* xc_list, const int* slot_list, const int* count_dev, int cap,
@@ -222,6 +223,13 @@ int mp_set_engine(int engine) {
   return 0;
 }
 int mp_get_engine(void) { return mp::g_engine; }
+
+int mp_set_precision(int mode) {
+  MP_REQUIRE(mode >= 0 && mode <= 2, "mp_set_precision: mode must be 0 (parity), 1 (single-term colour layers) or 2 (throughput)");
+  mp::g_precision.store(mode);
+  return 0;
+}
+int mp_get_precision(void) { return mp::g_precision.load(); }
 
 int mp_profile_enable(int on) { return mp::prof_enable(on); }
 int mp_set_streams(int on) {

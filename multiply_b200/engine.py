@@ -19,6 +19,12 @@ def set_engine(name):
     L.check(L.lib().mp_set_engine({"simt": 0, "tc": 1}[name]), "mp_set_engine")
 
 
+def set_precision(mode):
+    """tcgen05 engine precision: 'parity' (default, three split terms), 'colour1' (single-term colour layers),
+    'throughput' (single fp16 term everywhere; outside the 1e-4 gate)."""
+    L.check(L.lib().mp_set_precision({"parity": 0, "colour1": 1, "throughput": 2}[mode]), "mp_set_precision")
+
+
 def get_engine():
     return {0: "simt", 1: "tc"}[L.lib().mp_get_engine()]
 

@@ -249,6 +249,46 @@ def main():
         forward_case(ref, *case)
     rays_case(ref)
     grid_case(ref)
+    train_sampler_case(ref)
+
+
+def train_sampler_case(ref):
+    """ErrorBoundSampler.get_z_vals in TRAINING mode (model.training: stratified start samples, random final
+    abscissae, randperm extras, randint eikonal pick, jittered inverse-sphere samples; ray_sampler.py:32-40,171,202,
+    212-218; the SDF callback does not clamp outliers, multiply.py:142).  Every random tensor the reference draws is
+    recorded in draw order so that the port and the CUDA sampler can be fed the same numbers."""
+    sc = S.make_scene(P=2, S=16, seed=42)
+    m = build_ref_model(ref, sc)
+    m.train()
+    inputs = S.make_rays(sc, 40, seed=21, region="boxes")
+    hits = S.make_hit_lists(sc, inputs)
+    ray_dirs, cam_loc = ref.rend_util.get_camera_params(inputs["uv"], inputs["pose"], inputs["intrinsics"])
+    cam_loc = cam_loc.unsqueeze(1).repeat(1, ray_dirs.shape[1], 1).reshape(-1, 3)
+    ray_dirs = ray_dirs.reshape(-1, 3)
+    pid = 0
+    person = sc["persons"][pid]
+    idx = hits[pid].long()
+    draws = []
+    orig = (torch.rand, torch.randperm, torch.randint)
+
+    def rec(fn, tag):
+        def w(*a, **k):
+            out = fn(*a, **k)
+            draws.append((tag, out.clone()))
+            return out
+        return w
+    torch.rand, torch.randperm, torch.randint = rec(orig[0], "rand"), rec(orig[1], "randperm"), rec(orig[2], "randint")
+    try:
+        torch.manual_seed(1234)
+        (z_vals, z_bg), z_eik = m.ray_sampler.get_z_vals(ray_dirs[idx], cam_loc[idx], m, {"smpl": person["cond"]},
+                                                         person["tfs"][None], eval_mode=False,
+                                                         smpl_verts=person["verts_p"][None], person_id=pid)
+    finally:
+        torch.rand, torch.randperm, torch.randint = orig
+    tags = [t for t, _ in draws]
+    assert tags == ["rand", "rand", "randperm", "randint", "rand"], tags
+    save("sampler_train", hits=idx, t_rand=draws[0][1], u_final=draws[1][1], extra_perm=draws[2][1],
+         eik_idx=draws[3][1], t_rand_bg=draws[4][1], z_vals=z_vals, z_bg=z_bg, z_eik=z_eik, uv=inputs["uv"])
 
 
 def grid_case(ref):
@@ -326,5 +366,7 @@ if __name__ == "__main__":
             rays_case(_ref)
         if "sdf_grid" in sys.argv[2:]:
             grid_case(_ref)
+        if "sampler_train" in sys.argv[2:]:
+            train_sampler_case(_ref)
     else:
         main()

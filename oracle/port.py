@@ -221,15 +221,17 @@ def deform_inverse(x, person):
     return xc.squeeze(0), outlier
 
 
-def sdf_func_with_smpl_deformer(x, person, cfg, chunk=65536):
-    """Multiply.sdf_func_with_smpl_deformer (eval), lib/model/multiply.py:137-151."""
+def sdf_func_with_smpl_deformer(x, person, cfg, chunk=65536, training=False):
+    """Multiply.sdf_func_with_smpl_deformer, lib/model/multiply.py:137-151 (eval: outliers forced to 4, :142-143;
+    training: the network value everywhere)."""
     sdfs, xcs, feats = [], [], []
     for s in range(0, max(x.shape[0], 1), chunk):
         xs = x[s:s + chunk]
         x_c, outlier = deform_inverse(xs, person)
         out = implicit_forward(person["implicit"], x_c, person["cond"], cfg["multires"])
         sdf = out[:, 0:1].clone()
-        sdf[outlier] = 4.0
+        if not training:
+            sdf[outlier] = 4.0
         sdfs.append(sdf)
         xcs.append(x_c)
         feats.append(out[:, 1:])
@@ -363,16 +365,26 @@ def _error_bound(beta, sdf, z_vals, dists, d_star):
     return bound.max(-1)[0]
 
 
-def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=None, stats=None):
-    """ErrorBoundSampler.get_z_vals (eval mode, inverse_sphere_bg=True), ray_sampler.py:66-220.
+def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=None, stats=None, rng=None):
+    """ErrorBoundSampler.get_z_vals (inverse_sphere_bg=True), ray_sampler.py:66-220.
 
-    Returns (z_vals [R,S+X+2], z_bg [R,32]).  ``stats`` (dict) receives 'trips'."""
+    Eval mode (``rng is None``): returns (z_vals [R,S+X+2], z_bg [R,32]).
+    Training mode (``model.training``): every random draw of the reference is an INPUT (``rng``), in the order the
+    reference draws them —
+      t_rand [R,E]   stratified jitter of the uniform start samples      ray_sampler.py:32-40
+      u_final [R,S]  the inverse-CDF abscissae of the final sample set   :171
+      extra_perm [M] torch.randperm(M) whose first X entries pick the extra samples (M = trips * E)   :202
+      eik_idx [R]    torch.randint(S+X+2, (R,)) for z_samples_eik         :212-213
+      t_rand_bg [R,32]  jitter of the inverse-sphere samples (the UniformSampler sees model.training too)   :216
+    — the SDF callback does not clamp outliers (multiply.py:142 is eval-only) and the return is
+    (z_vals, z_bg, z_samples_eik [R,1]).  ``stats`` (dict) receives 'trips'."""
     S, E, X = cfg["N_samples"], cfg["N_samples_eval"], cfg["N_samples_extra"]
     eps, beta_iters, max_iters = cfg["eps"], cfg["beta_iters"], cfg["max_total_iters"]
     add_tiny, bound_r = cfg["add_tiny"], cfg["scene_bounding_sphere"]
     near_v = cfg.get("near", 0.0)
+    training = rng is not None
     if sdf_fn is None:
-        sdf_fn = lambda pts: sdf_func_with_smpl_deformer(pts, person, cfg)[0]
+        sdf_fn = lambda pts: sdf_func_with_smpl_deformer(pts, person, cfg, training=training)[0]
     R = ray_dirs.shape[0]
     beta0 = get_beta(beta_param)
 
@@ -382,6 +394,11 @@ def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=No
     far = si[:, 1:]
     t_vals = torch.linspace(0., 1., steps=E)
     z_vals = near * (1. - t_vals) + far * t_vals
+    if training:      # ray_sampler.py:32-40
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        z_vals = lower + (upper - lower) * rng["t_rand"]
     samples, samples_idx = z_vals, None
 
     dists = z_vals[:, 1:] - z_vals[:, :-1]
@@ -455,7 +472,10 @@ def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=No
             cdf = torch.cumsum(pdf, -1)
             cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
 
-        u = torch.linspace(0., 1., steps=N).unsqueeze(0).repeat(cdf.shape[0], 1).contiguous()
+        if (not_converge and total_iters < max_iters) or not training:      # ray_sampler.py:166-170
+            u = torch.linspace(0., 1., steps=N).unsqueeze(0).repeat(cdf.shape[0], 1).contiguous()
+        else:
+            u = rng["u_final"].contiguous()
         inds = torch.searchsorted(cdf, u, right=True)
         below = torch.max(torch.zeros_like(inds - 1), inds - 1)
         above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
@@ -478,7 +498,11 @@ def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=No
     near = near_v * torch.ones(R, 1)
     far = get_sphere_intersections(cam_loc, ray_dirs, r=bound_r)[:, 1:]
     if X > 0:
-        sampling_idx = torch.linspace(0, z_vals.shape[1] - 1, X).long()
+        if training:
+            assert rng["extra_perm"].shape[0] == z_vals.shape[1], "randperm(M) was drawn for another trip count"
+            sampling_idx = rng["extra_perm"][:X].long()
+        else:
+            sampling_idx = torch.linspace(0, z_vals.shape[1] - 1, X).long()
         z_extra = torch.cat([near, far, z_vals[:, sampling_idx]], -1)
     else:
         z_extra = torch.cat([near, far], -1)
@@ -486,8 +510,15 @@ def error_bound_get_z_vals(ray_dirs, cam_loc, person, cfg, beta_param, sdf_fn=No
 
     # inverse-sphere background samples: UniformSampler(1.0, 0.0, 32, False, far=1.0), ray_sampler.py:215-218
     tb = torch.linspace(0., 1., steps=32)
-    z_bg = (torch.zeros(R, 1) * (1. - tb) + torch.ones(R, 1) * tb) * (1. / bound_r)
-    return z_out, z_bg
+    z_bg = torch.zeros(R, 1) * (1. - tb) + torch.ones(R, 1) * tb
+    if training:
+        z_eik = torch.gather(z_out, 1, rng["eik_idx"].long().unsqueeze(-1))      # ray_sampler.py:212-213
+        mids = .5 * (z_bg[..., 1:] + z_bg[..., :-1])
+        upper = torch.cat([mids, z_bg[..., -1:]], -1)
+        lower = torch.cat([z_bg[..., :1], mids], -1)
+        z_bg = lower + (upper - lower) * rng["t_rand_bg"]
+        return z_out, z_bg * (1. / bound_r), z_eik
+    return z_out, z_bg * (1. / bound_r)
 
 
 # --------------------------------------------------------------------------------------

@@ -58,4 +58,4 @@ for eng in ("simt", "tc"):
             dn = torch.where(same, dn, torch.zeros_like(dn))
             print(eng, "person", p, "per-sample normal max", float(dn.max()), "mean", float(dn.mean()),
                   "count>1e-4", int((dn > 1e-4).sum()), "of", int(same.sum()))
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "normal_diag.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "normal_diag_%s.json" % os.environ.get("MP_TC_RZ_SCALE", "default")), "w"), indent=1)

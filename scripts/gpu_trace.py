@@ -1,6 +1,6 @@
 """Print the cycle stamps of one tile of CTA 0 of the tcgen05 chain (MP_TC_KNOBS=2), shade program of bench config 2."""
 import os, ctypes as C
-os.environ["MP_TC_KNOBS"] = "2"
+os.environ["MP_TC_KNOBS"] = os.environ.get("MP_TC_KNOBS", "2")
 import torch
 from multiply_b200 import _lib as L
 from multiply_b200.scene import make_scene, make_rays, make_hit_lists

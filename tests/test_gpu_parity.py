@@ -81,7 +81,8 @@ def test_camera_rays_and_sphere(golden_dir):
     assert _maxabs(nf.cpu().numpy(), g["near_far"]) < 2e-6
     # a camera outside the sphere: the reference exits (rend_util.py:140-142), the mirror raises
     with pytest.raises(RuntimeError):
-        rend_util.get_sphere_intersections(cam_r * 10.0, torch.from_numpy(g["ray_dirs"][0]).cuda(), r=3.0)
+        rend_util.get_sphere_intersections(cam_r + torch.tensor([50.0, 0.0, 0.0], device="cuda"),
+                                           torch.from_numpy(g["ray_dirs"][0]).cuda(), r=3.0)
 
 
 @pytest.mark.parametrize("eng", ENGINES)
@@ -133,7 +134,7 @@ def test_sphere_status_flag():
     r = engine.Renderer(sc)
     r.render(inp, hits, check=True)
     far = dict(inp, pose=inp["pose"].clone())
-    far["pose"][0, :3, 3] *= 4.0
+    far["pose"][0, 0, 3] = 10.0            # camera moved sideways: its rays pass the r = 3 sphere by
     with pytest.raises(RuntimeError, match="BOUNDING SPHERE"):
         r.render(far, hits, check=True)
 

@@ -127,3 +127,25 @@ def test_sdf_grid(golden_dir, scene64):
     vals, pts = port.sdf_grid(p1, dict(scene64["cfg"], multires=6), p1["verts_c"], int(g["res"]))
     assert np.array_equal(pts, g["points"])
     assert np.abs(vals.numpy().reshape(-1) - g["occ"]).max() < 2e-6
+
+
+def test_sampler_training_mode(golden_dir):
+    """port.error_bound_get_z_vals in TRAINING mode (random draws fed in as tensors) against the reference's
+    ErrorBoundSampler.get_z_vals with model.training set: sample depths, jittered inverse-sphere depths, eikonal pick."""
+    g = _g(golden_dir, "sampler_train")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inputs = dict(S.make_rays(sc, 40, seed=21, region="boxes"))
+    assert np.array_equal(inputs["uv"].numpy(), g["uv"])
+    dirs, cam = port.get_camera_params(inputs["uv"], inputs["pose"], inputs["intrinsics"])
+    cam = cam.unsqueeze(1).repeat(1, dirs.shape[1], 1).reshape(-1, 3)
+    dirs = dirs.reshape(-1, 3)
+    idx = torch.from_numpy(g["hits"])
+    rng = {k: torch.from_numpy(g[k]) for k in ("t_rand", "u_final", "extra_perm", "eik_idx", "t_rand_bg")}
+    st = {}
+    z, z_bg, z_eik = port.error_bound_get_z_vals(dirs[idx], cam[idx], sc["persons"][0], sc["cfg"], sc["beta_param"],
+                                                 stats=st, rng=rng)
+    assert st["trips"] * sc["cfg"]["N_samples_eval"] == g["extra_perm"].shape[0]
+    assert np.abs(z_bg.numpy() - g["z_bg"]).max() < 1e-7
+    dz = np.abs(z.numpy() - g["z_vals"])
+    assert np.median(dz) < 1e-6 and dz.max() < 5e-3          # coarse 16/32/8 sampler: see test_forward_golden_coarse
+    assert np.abs(z_eik.numpy() - g["z_eik"]).max() < 5e-3

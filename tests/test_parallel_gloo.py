@@ -113,3 +113,77 @@ def test_person_rows_exchange_gloo():
         for p in procs:
             p.join(timeout=60)
         assert all(ok for _, ok in res), res
+
+
+# ---- PixelBuffer: outputs written straight into the gather buffer, one all_gather_into_tensor, no concatenation ----
+def _pixbuf_worker(rank, world, port, R, P, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    inputs = {"uv": torch.rand(1, R * world, 2, generator=g) * 512}
+    mine = inputs["uv"][:, rank * R:(rank + 1) * R]
+    buf = parallel.PixelBuffer(R, P, torch.device("cpu"))
+    out = _fake_render(mine, P)
+    for k in parallel.PIXEL_KEYS:
+        assert buf.views[k].is_contiguous() and buf.views[k].shape == out[k].shape
+        buf.views[k].copy_(out[k])            # stands in for Renderer.render(out=buf.views)
+    gathered = torch.empty(world, R * (10 + P))
+    dist.all_gather([gathered[r] for r in range(world)], buf.flat)    # NCCL path: all_gather_into_tensor(gathered, buf.flat)
+    frame = parallel.PixelBuffer.frame(gathered, world, R, P)
+    ref = _fake_render(inputs["uv"], P)
+    q.put((rank, all(torch.equal(frame[k], ref[k]) for k in parallel.PIXEL_KEYS)))
+    dist.destroy_process_group()
+
+
+def test_pixel_buffer_all_gather_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pixbuf_worker, args=(r, world, port, 333, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+# ---- the exchange inside a SUB-group: P2POp peers must be global ranks (ranks 1 and 2 of a 3-rank world) ----
+def _subgroup_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grp = dist.new_group([1, 2])
+    ok = True
+    if rank in (1, 2):
+        gr, gw = dist.get_rank(grp), 2
+        g = torch.Generator().manual_seed(5)
+        total, P, width = 300, 3, 5
+        hits = [torch.sort(torch.randperm(total, generator=g)[: 40 + 30 * p])[0] for p in range(P)]
+        full = [torch.rand(h.numel(), width, generator=g) for h in hits]
+        plan = parallel.exchange_plan(hits, total, gw)
+        rows = {p: full[p] for p in range(P) if parallel.person_owner(p, gw) == gr}
+        got = parallel.exchange_person_rows(rows, plan, width, gr, gw, torch.device("cpu"), grp)
+        lo, hi = parallel.shard_bounds(total, gr, gw)
+        for p in range(P):
+            sel = (hits[p] >= lo) & (hits[p] < hi)
+            ok = ok and torch.equal(got[p], full[p][sel])
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_person_rows_exchange_in_subgroup_gloo():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
