@@ -367,6 +367,8 @@ def main():
     ap.add_argument("--engine", default=os.environ.get("MP_ENGINE", "tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--precision", default="parity", choices=["parity", "colour1", "throughput"],
+                    help="tcgen05 precision mode of the main measurement (default parity: RGB/SDF within 1e-4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -384,6 +386,7 @@ def main():
     from multiply_b200 import engine, parallel, scene as S, _lib as L
     lib = L.lib()
     engine.set_engine(args.engine)
+    engine.set_precision(args.precision)
     # ---- workload: the drop-in scene (bodies from the device SMPL server) --------------------------------
     sc, model, smpl_in = S.make_smpl_scene(P=PERSONS, S=S_SAMPLES, seed=42, device=dev)
     full = S.make_rays(sc, RAYS_PER_GPU * world, seed=1234, region="boxes")

@@ -239,6 +239,25 @@ int mp_sample_rays(const mp_sampler_cfg_t* cfg, mp_body_t* body, mp_net_t* field
                    float* z_vals, float* z_bg, int* trips_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training-mode get_z_vals (model.training: ray_sampler.py:32-40 stratified start samples, :171 random abscissae of the
+ * final set, :202 randperm extras, :212-213 the eikonal pick, :216 jittered inverse-sphere depths; the SDF callback does
+ * not clamp outliers, multiply.py:142).  Every random draw of the reference is an INPUT so that a caller can replay the
+ * reference's RNG stream.  The draws made after the Algorithm-1 loop depend on the number of trips T+1 the loop took
+ * (randperm((T+1) E), and the generator state after it), which only the device knows: they are passed for EVERY possible
+ * T and the kernels pick the row of the trip the loop ended on.  T_max = cfg->max_total_iters. */
+typedef struct {
+  const float* t_rand;     /* [R, E]                      torch.rand of UniformSampler.get_z_vals */
+  const float* u_final;    /* [R, S]                      torch.rand at the final inverse-CDF step */
+  const int* extra_perm;   /* [T_max, T_max*E] int32      row T: torch.randperm((T+1)*E), first X entries are used */
+  const int* eik_idx;      /* [T_max, R] int32            row T: torch.randint(S+X+2, (R,)) */
+  const float* t_rand_bg;  /* [T_max, R, 32] or NULL      row T: torch.rand of the inverse-sphere UniformSampler */
+} mp_sampler_rng_t;
+/* outputs as mp_sample_rays plus z_eik [R] (z_samples_eik, may be NULL) */
+int mp_sample_rays_train(const mp_sampler_cfg_t* cfg, mp_body_t* body, mp_net_t* field,
+                         const float* ray_dirs, const float* cam_loc, int R, const mp_sampler_rng_t* rng,
+                         float* z_vals, float* z_bg, float* z_eik, int* trips_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Multiply.sdf_func_with_smpl_deformer (multiply.py:137-151, eval): x [N,3] -> sdf [N] (4.0 on outliers),
  * x_c [N,3], feat [N,256] (may be NULL). */
 int mp_sdf_with_deformer(mp_body_t* body, mp_net_t* field, const float* x, int N,

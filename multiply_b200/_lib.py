@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmultiply_b200.so")
+LIB_PATH = os.environ.get("MP_LIB") or os.path.join(HERE, "libmultiply_b200.so")     # MP_LIB: A/B builds (scripts/)
 
 MP_MAX_LAYERS = 12
 MP_MAX_PERSONS = 8
@@ -44,6 +44,11 @@ class SamplerCfg(C.Structure):
                 ("N_samples_eval", C.c_int), ("N_samples_extra", C.c_int), ("eps", C.c_float),
                 ("beta_iters", C.c_int), ("max_total_iters", C.c_int), ("add_tiny", C.c_float),
                 ("beta_param", C.c_float), ("beta_min", C.c_float)]
+
+
+class SamplerRng(C.Structure):
+    _fields_ = [("t_rand", C.c_void_p), ("u_final", C.c_void_p), ("extra_perm", C.c_void_p), ("eik_idx", C.c_void_p),
+                ("t_rand_bg", C.c_void_p)]
 
 
 class PersonSamples(C.Structure):
@@ -113,6 +118,8 @@ SIGNATURES = {
     "mp_smpl_forward": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_sampler_workspace_bytes": (_SZ, [C.POINTER(SamplerCfg), _I]),
     "mp_sample_rays": (_I, [C.POINTER(SamplerCfg), _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mp_sample_rays_train": (_I, [C.POINTER(SamplerCfg), _VP, _VP, _VP, _VP, _I, C.POINTER(SamplerRng), _VP, _VP, _VP, _VP,
+                                  _VP, _SZ, _VP]),
     "mp_sdf_with_deformer": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mp_composite_workspace_bytes": (_SZ, [_I, _I]),
     "mp_composite": (_I, [C.POINTER(PersonSamples), _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -98,12 +98,13 @@ struct TcIO {
 constexpr size_t kSigBytes = (size_t)8 * 64 * 128 * 16;      // sigma' [8][64][128] float4
 constexpr size_t kFeatBytes = (size_t)2 * 32 * 128 * 16;     // features hi/lo chunks
 constexpr size_t kGeBytes = (size_t)96 * 128 * 4;            // skip gradient [E<=96][128]
+constexpr size_t kMiscBytes = (size_t)128 * 32 * 4;          // partial sums / normals [128][32]
 constexpr size_t kEmbBytes = (size_t)96 * 128 * 4;           // input embedding of the tile [E<=96][128]
-constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kEmbBytes;
+constexpr size_t kScratchPerCta = kSigBytes + kFeatBytes + kGeBytes + kMiscBytes + kEmbBytes;
 
 // shared memory carve-up
 constexpr int kABytes = 2 * 4 * 128 * 128;                   // hi + lo, 4 K-blocks of [128 x 128B]
-constexpr int kXchBytes = 3 * 128 * 4;                        // partial dots of column parts 1..3 (sdf), [3][128] floats
+constexpr int kXchBytes = 2 * 128 * 4;                        // d sdf / d x_1, d x_2 of the tile's rows (final-gradient step)
 constexpr int kSmemBytes = kABytes + kRing * kSlotBytes + 256 + kXchBytes + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget of one CTA (227 KB)");
 
@@ -249,11 +250,6 @@ __device__ __forceinline__ void discard_line(const void* p, float dep) {
 __device__ __forceinline__ void discard_line(const void* p, uint32_t dep) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(p), "r"(dep) : "memory");
 }
-// asymmetric named barrier: producers arrive and run on, the consumer part waits
-template <int N>
-__device__ __forceinline__ void xbar_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void xbar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(N) : "memory"); }
 
 template <int N>
 __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
@@ -350,6 +346,16 @@ __device__ __forceinline__ void tmem_wait<32>(float* v) {
                : "memory");
 }
 
+// Step kinds: the chunk loop of a layer step is compiled once per kind (compile-time tag), so that every kind gets its own
+// instruction schedule and register allocation instead of one loop that tests the step descriptor in its body.  (The
+// single generic loop of round 1 was at the mercy of the optimiser: unrelated edits elsewhere in the kernel moved the
+// forward steps between 13.5 k and 18 k cycles.)
+enum { K_SP_PLAIN = 0, K_SP_SAVE = 1, K_SP_SEED = 2, K_FEAT = 3, K_BWD = 4, K_RELU = 5 };
+template <int K>
+struct KTag {
+  static constexpr int value = K;
+};
+
 // cycle stamps of CTA 0 (MP_TC_KNOBS bit 1): [0..] epilogue warp 2, [2048..] MMA issuer; see mp_tc_trace_read
 __device__ unsigned long long g_trace[4096];
 
@@ -366,7 +372,7 @@ __device__ unsigned long long g_trace[4096];
 template <int NW, bool PIPE>
 __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_constant__ TcProgram P,
                                                                    const __grid_constant__ TcIO io) {
-  static_assert(PIPE && NW == 16, "the shipped kernel: four column parts of 16-column chunks, K-block-granular hand-over");
+  static_assert(!PIPE || NW == 16, "PIPE needs four column parts of 16-column chunks");
   constexpr int NBAR = PIPE ? 4 : 1;       // operand hand-over barriers (one per K-block when pipelined)
   constexpr int TCOLS = PIPE ? 512 : 256;  // TMEM columns
   constexpr int NPART = NW / 4;            // column parts
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   uint64_t* x_free = bars + 2 * kRing + 1 + NBAR;      // K-block 0 of A drained by the MMAs (extra-input steps)
   uint64_t* x_ready = x_free + 1;                      // extra inputs staged there
   uint32_t* tmem_slot = (uint32_t*)(x_ready + 1);
-  float* xs = (float*)((char*)bars + 256);             // [3][128] partial sdf dots of column parts 1..3
+  float* xs = (float*)((char*)bars + 256);             // [2][128] exchange of the final-gradient step
 
   const int count = io.count ? min(io.cap, *io.count) : io.cap;
   const int ntiles = (count + 127) >> 7;
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         for (int s = 0; s < P.nsteps; ++s) {
           const char* src = (const char*)P.blob + (size_t)P.step[s].slot_off * kSlotBytes;
           const int nslot = 2 * P.step[s].nk;
-          const int jstep = P.step[s].terms == 1 ? 2 : 1;     // single-term steps skip the W_lo slots
+          const int jstep = P.step[s].terms == 1 ? 2 : 1;
           for (int j = 0; j < nslot; j += jstep, ++it) {
             int r = it % kRing;
             uint32_t ph = (it / kRing) & 1;
@@ -476,16 +482,16 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             umma_commit(&empty[r]);
             ++it;
             if (!one_term) {
-              // lo slot: A_hi.W_lo
-              r = it % kRing;
-              mbar_wait(&full[r], (it / kRing) & 1);
-              tc_fence_after();
-              wb = smem_u32(ring + (size_t)r * kSlotBytes);
+            // lo slot: A_hi.W_lo
+            r = it % kRing;
+            mbar_wait(&full[r], (it / kRing) & 1);
+            tc_fence_after();
+            wb = smem_u32(ring + (size_t)r * kSlotBytes);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-              umma_commit(&empty[r]);
-              ++it;
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(tmem, make_desc(a_hi + (kc & 3) * 16384 + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+            umma_commit(&empty[r]);
+            ++it;
             }
             if (kc == 0 && nk == 5) umma_commit(x_free);   // K-block 0 may be overwritten once these have completed
           }
@@ -511,7 +517,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     float4* sig = (float4*)scr;                                  // [8][64][128]
     uint4* fsc = (uint4*)(scr + kSigBytes);                      // [2][32][128]
     float* ge = (float*)(scr + kSigBytes + kFeatBytes);          // [96][128]
-    float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);    // [96][128]
+    float* misc = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes);   // [128][32]
+    float* emb = (float*)(scr + kSigBytes + kFeatBytes + kGeBytes + kMiscBytes);   // [96][128]
     uint32_t df_ph = 0, xf_ph = 0;
     const int d = P.d_in, E = P.E;
     const int cbeg = part * PCOLS;
@@ -584,6 +591,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         // reverse-sweep steps: start fetching sigma' of the first chunk before blocking on the accumulator
         float4 s4[G4];
         const bool need_sig = (st.epi == EPI_BWD) && st.sig >= 0;
+#pragma unroll
+        for (int g4 = 0; g4 < G4; ++g4) s4[g4] = make_float4(0.f, 0.f, 0.f, 0.f);      // (always initialised: see b4 below)
         if (need_sig) {
 #pragma unroll
           for (int g4 = 0; g4 < G4; ++g4) s4[g4] = ld_stream(&sig[((size_t)st.sig * 64 + ((col_of(0) >> 2) + g4)) * 128 + row]);
@@ -612,31 +621,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           }
           fence_async_smem();
           mbar_arrive(x_ready);
-        }
-        // Final step of the reverse sweep.  B0's output columns are permuted at pack time BY AXIS: column part a
-        // (a < d_in) holds, in its 16 columns of K-block 0, every embedding index that depends on x_a --
-        // [x_a, sin(2^0 x_a), cos(2^0 x_a), sin(2^1 x_a), ...] (embedders.py:8-34) -- so the chain rule
-        //   d sdf / d x_a = sum_k (g_k + skip_k) * d embed_k / d x_a
-        // of one axis runs inside one thread's registers, and the only exchange between warps is one float per row and
-        // axis through shared memory.  The skip gradient (parked at the F_SKIP_GRAD step) and the partner sin / cos of
-        // each index (parked by the tile prologue) are fetched before blocking on the accumulator.
-        const bool fin = (st.flags & F_FINAL_GRAD) != 0;
-        const bool fin_owner = fin && part < d;
-        constexpr int FN = 14;                         // indices per axis: 1 + 2 * multires <= 13 for multires <= 6 (+ pad)
-        float pg[FN], pe[FN];
-        if (fin_owner) {
-#pragma unroll
-          for (int j = 0; j < FN; ++j) {
-            // j = 0: x_a itself; j = 1 + 2 f: sin(2^f x_a); j = 2 + 2 f: cos(2^f x_a)
-            const int fq = (j - 1) >> 1;
-            const int k = (j == 0) ? part : d + 2 * fq * d + ((j - 1) & 1) * d + part;
-            const bool ok = j < 1 + 2 * P.multires;
-            pg[j] = ok ? ge[(size_t)k * 128 + row] : 0.f;
-            // partner: cos for a sin entry (+d), sin for a cos entry (-d)
-            pe[j] = (ok && j > 0) ? emb[(size_t)(((j - 1) & 1) ? k - d : k + d) * 128 + row] : 0.f;
-          }
-          if (part == 0 && io.jinv && valid)      // the inverse Jacobian is cold (written by the deformer kernel): pull it in
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(io.jinv + 12 * (size_t)pt));
         }
         const bool tr = (io.knobs & 2) && blockIdx.x == 0 && warp == 2 && lane == 0 && tile == (int)(blockIdx.x + gridDim.x);
         unsigned long long* trp = g_trace + (P.nsteps > 12 ? 0 : 1024) + s * 8;
@@ -686,17 +670,21 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
         auto issue_next = [&](const int ci) {
           if (ci + 1 < NCH) tmem_issue<CW>(t_row + (uint32_t)col_of(ci + 1), va);
         };
-        auto process_chunk = [&](float* v, const int ci) {
+        auto process_chunk = [&](auto ktag, float* v, const int ci) {
+          constexpr int KIND = decltype(ktag)::value;
           const int c = col_of(ci);
           // the bias of this chunk is fetched under the TMEM load
+          // (loaded unconditionally where the kind uses it and not declared live otherwise: a conditionally initialised
+          // array makes the compiler keep it in local memory -- 8 local loads / stores per chunk, measured 13.5 k -> 20 k
+          // cycles per forward step)
           float4 b4[G4];
-          if (st.bias) {
+          if constexpr (KIND != K_BWD) {
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) b4[g4] = __ldg((const float4*)(st.bias + c + 4 * g4));
           }
           tmem_wait<CW>(v);
-          if (st.epi == EPI_SOFTPLUS) {
-            if ((st.flags & (F_SAVE_SIG | F_SEED_BWD)) == (F_SAVE_SIG | F_SEED_BWD)) {
+          if constexpr (KIND == K_SP_PLAIN || KIND == K_SP_SAVE || KIND == K_SP_SEED) {
+            if constexpr (KIND == K_SP_SEED) {
               // last SDF layer of the fused chain: sigma'_7 is consumed right here -- the reverse sweep starts from
               // A = W8[0,:] * sigma'_7 (d sdf / d z7), h7 only feeds the sdf dot and the feature stash
               float seed[CW];
@@ -732,7 +720,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               }
               return;
             }
-            if (st.flags & F_SAVE_SIG) {
+            if constexpr (KIND == K_SP_SAVE) {
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4) {
                 float dd[4];
@@ -766,7 +754,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 dot0 = fmaf(v[4 * g4 + 3], w4.w, dot0);
               }
             }
-          } else if (st.epi == EPI_FEAT) {
+          } else if constexpr (KIND == K_FEAT) {
 #pragma unroll
             for (int g4 = 0; g4 < G4; ++g4) {
               const float4 b = b4[g4];
@@ -780,7 +768,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               for (int j = 0; j < CW; j += 4)
                 *(float4*)(io.feat_out + (size_t)pt * 256 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-          } else if (st.epi == EPI_BWD) {
+          } else if constexpr (KIND == K_BWD) {
             if ((st.flags & F_SKIP_GRAD) && c + CW > P.inj_col) {
               // columns >= inj_col are d/d embed through the skip connection: park them, zero them in A
               const float* s4f = reinterpret_cast<const float*>(s4);
@@ -803,7 +791,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                 v[4 * g4 + 3] *= isc * s4[g4].w;
               }
             }
-            if (need_sig && (lane & 7) == 0 && !(io.knobs & 4)) {   // this chunk's sigma' lines are dead: drop them from L2 without write-back
+            if (need_sig && (lane & 7) == 0 && !(io.knobs & 4)) {   // this chunk's sigma' lines are dead: drop them from L2
 #pragma unroll
               for (int g4 = 0; g4 < G4; ++g4)
                 discard_line(&sig[((size_t)st.sig * 64 + ((c >> 2) + g4)) * 128 + row], v[4 * g4]);
@@ -858,66 +846,61 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             issue_next(ci);
           }
         };
-        float gax = 0.f;                                // d sdf / d x_part (column parts 0..d-1, final step)
-        if (fin) {
-          // only column parts 0..d-1 have anything to drain, in their first chunk (the rest of B0's columns is padding)
-          if (fin_owner) {
+        if (st.flags & F_FINAL_GRAD) {
+          // ---- last step of the reverse sweep: its own straight-line code (everything it needs lives only here, so the
+          // hot chunk loops of the other steps do not carry its registers) ----
+          // B0's output columns are permuted at pack time BY AXIS: column part a (a < d_in) holds, in its 16 columns of
+          // K-block 0, every embedding index that depends on x_a -- [x_a, sin(2^0 x_a), cos(2^0 x_a), sin(2^1 x_a), ...]
+          // (embedders.py:8-34) -- so the chain rule
+          //   d sdf / d x_a = sum_k (g_k + skip_k) * d embed_k / d x_a
+          // of one axis runs inside one thread's registers.  The skip gradient (parked at the F_SKIP_GRAD step) and the
+          // partner sin / cos of each index (parked by the tile prologue) come from scratch: independent loads issued
+          // together under the TMEM load.
+          float gax = 0.f;                                 // d sdf / d x_part (column parts 0..d-1)
+          if (part < d) {
             tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
+            float pg[14], pe[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+              // j = 0: x_a itself; j = 1 + 2 f: sin(2^f x_a); j = 2 + 2 f: cos(2^f x_a)
+              const int fq = (j - 1) >> 1;
+              const int k = (j == 0) ? part : d + 2 * fq * d + ((j - 1) & 1) * d + part;
+              const bool ok = j < 1 + 2 * P.multires;
+              pg[j] = ok ? ge[(size_t)k * 128 + row] : 0.f;
+              // partner: cos for a sin entry (+d), sin for a cos entry (-d)
+              pe[j] = (ok && j > 0) ? emb[(size_t)(((j - 1) & 1) ? k - d : k + d) * 128 + row] : 0.f;
+            }
             tmem_wait<CW>(va);
 #pragma unroll
-            for (int j = 0; j < FN; ++j) {
-              const float tot = fmaf(va[j], isc, pg[j]);             // through layer 0 + through the skip connection
+            for (int j = 0; j < 14; ++j) {
+              const float tot = fmaf(va[j], isc, pg[j]);           // through layer 0 + through the skip connection
               const int fq = (j - 1) >> 1;
               // d x / d x = 1 ; d sin(2^f x) = 2^f cos(2^f x) ; d cos(2^f x) = -2^f sin(2^f x)
               const float w = (j == 0) ? 1.f : (float)(1 << fq) * (((j - 1) & 1) ? -pe[j] : pe[j]);
               gax = fmaf(w, tot, gax);
             }
-            if (tr) trp[2] = clock64();
           }
-        } else {
-          // (a second register buffer for the TMEM reads was measured slower: +20 % kernel time from spills / code size)
-          tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
-#pragma unroll 1
-          for (int ci = 0; ci < NCH; ++ci) {
-            process_chunk(va, ci);
-            if (tr) trp[2 + ci] = clock64();
-            if (chunk_handover) {
-              // K-block ci of the next layer's operand is complete in this thread
-              fence_async_smem();
-              tc_fence_before();
-              mbar_arrive(&a_ready[ci]);
-            }
-          }
-        }
-        tc_fence_before();
-        // ---- step-specific tails ----
-        if (st.flags & F_SDF_DOT) {
-          // partial dots of column parts 1..3 -> shared memory; they arrive and run on, part 0 waits, sums in part
-          // order and writes the SDF.  (xs is next written a whole tile -- many barriers -- later.)
-          if (part != 0) {
-            xs[(part - 1) * 128 + row] = dot0;
-            xbar_arrive<NEPI>();
-          } else {
-            xbar_sync<NEPI>();
-            if (valid && io.sdf_out) {
-              float sacc = __ldg(P.b8) + dot0;
-#pragma unroll
-              for (int pp = 0; pp < NPART - 1; ++pp) sacc += xs[pp * 128 + row];
-              io.sdf_out[slot] = sacc;
-            }
-          }
-        }
-        if (st.flags & F_SKIP_GRAD) __threadfence_block();
-        if (fin) {
+          tc_fence_before();
           if (tr) g_trace[513] = clock64();
           // axes 1..d-1 travel to column part 0 through shared memory (one float per row); it derives
           // normal = normalize(g . J^-1) (multiply.py:661), normalised again with eps 1e-6 (:606), writes the outputs and
           // is the part that stages the colour net's extra inputs [x_c, n].  Parts 1.. go on without waiting.
+          // (Round 1 exchanged every term through global scratch behind two 512-thread barriers: 30 k cycles per tile.)
           float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-          if (fin_owner && part != 0) {
-            xs[(part - 1) * 128 + row] = gax;
-            asm volatile("bar.arrive 4, %0;" ::"r"(128 * d) : "memory");
-          } else if (part == 0) {
+          if (part != 0) {
+            if (part < d) {
+              xs[(part - 1) * 128 + row] = gax;
+              asm volatile("bar.arrive 4, %0;" ::"r"(128 * d) : "memory");
+            }
+          } else {
+            // the inverse Jacobian of this row's point (cold: written by the deformer kernel) travels under the barrier
+            float4 ja = make_float4(0.f, 0.f, 0.f, 0.f), jb = ja, jc = ja;
+            if (io.jinv && valid) {
+              const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
+              ja = __ldg(J4);      // J[0..3]
+              jb = __ldg(J4 + 1);  // J[4..7]
+              jc = __ldg(J4 + 2);  // J[8..11]
+            }
             asm volatile("bar.sync 4, %0;" ::"r"(128 * d) : "memory");
             const float gx0 = gax, gx1 = d > 1 ? xs[row] : 0.f, gx2 = d > 2 ? xs[128 + row] : 0.f;
             if (io.grad_out && valid) {
@@ -926,8 +909,6 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               io.grad_out[3 * (size_t)pt + 2] = gx2;
             }
             if (io.jinv && valid) {
-              const float4* J4 = (const float4*)(io.jinv + 12 * (size_t)pt);
-              const float4 ja = __ldg(J4), jb = __ldg(J4 + 1), jc = __ldg(J4 + 2);      // J[0..3], J[4..7], J[8..11]
               float v0 = gx0 * ja.x + gx1 * ja.w + gx2 * jb.z;
               float v1 = gx0 * ja.y + gx1 * jb.x + gx2 * jb.w;
               float v2 = gx0 * ja.z + gx1 * jb.y + gx2 * jc.x;
@@ -948,28 +929,69 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           nrm[1] = n1;
           nrm[2] = n2;
           if (tr) g_trace[517] = clock64();
+          // hand-over: the features already went back into A (reload_features above); nothing else to arrive on
+          if (tr) trp[6] = clock64();
+          continue;
         }
+        // (a second register buffer for the TMEM reads was measured slower: +20 % kernel time from spills / code size)
+        auto run_chunks = [&](auto ktag) {
+          tmem_issue<CW>(t_row + (uint32_t)col_of(0), va);
+#pragma unroll 1
+          for (int ci = 0; ci < NCH; ++ci) {
+            process_chunk(ktag, va, ci);
+            if (tr) trp[2 + ci] = clock64();
+            if (chunk_handover) {
+              // K-block ci of the next layer's operand is complete in this thread
+              fence_async_smem();
+              tc_fence_before();
+              mbar_arrive(&a_ready[ci]);
+            }
+          }
+        };
+        if (st.epi == EPI_SOFTPLUS) {
+          if ((st.flags & (F_SAVE_SIG | F_SEED_BWD)) == (F_SAVE_SIG | F_SEED_BWD))
+            run_chunks(KTag<K_SP_SEED>{});
+          else if (st.flags & F_SAVE_SIG)
+            run_chunks(KTag<K_SP_SAVE>{});
+          else
+            run_chunks(KTag<K_SP_PLAIN>{});
+        } else if (st.epi == EPI_FEAT) {
+          run_chunks(KTag<K_FEAT>{});
+        } else if (st.epi == EPI_BWD) {
+          run_chunks(KTag<K_BWD>{});
+        } else {
+          run_chunks(KTag<K_RELU>{});
+        }
+        tc_fence_before();
+        // ---- step-specific tails ----
+        if (st.flags & F_SDF_DOT) {
+          misc[row * 32 + part] = dot0;
+          __threadfence_block();
+          ep_bar<NEPI>();
+          if (part == 0 && valid && io.sdf_out) {
+            float sacc = __ldg(P.b8);
+#pragma unroll
+            for (int pp = 0; pp < NPART; ++pp) sacc += misc[row * 32 + pp];
+            io.sdf_out[slot] = sacc;
+          }
+          // (no second barrier: these scratch slots are next written a whole tile -- many barriers -- later)
+        }
+        if (st.flags & F_SKIP_GRAD) __threadfence_block();
         if (st.flags & F_RGB_OUT) {
           // last step of the tile: the MMAs are done with A, its K-block 3 serves as the exchange buffer for the
-          // partial dots (the next write there is a whole layer step -- and several barriers -- away); parts 1..3 arrive
-          // and go on to the next tile's prologue, part 0 sums in part order
+          // partial dots (the next write there is a whole layer step -- and several barriers -- away)
           float* xch = reinterpret_cast<float*>(A + 3 * 16384);
-          if (part != 0) {
-            xch[(part * 3 + 0) * 128 + row] = dot0;
-            xch[(part * 3 + 1) * 128 + row] = dot1;
-            xch[(part * 3 + 2) * 128 + row] = dot2;
-            asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
-          } else {
-            asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
-            if (valid && io.rgb_out) {
-              const float dk[3] = {dot0, dot1, dot2};
+          xch[(part * 3 + 0) * 128 + row] = dot0;
+          xch[(part * 3 + 1) * 128 + row] = dot1;
+          xch[(part * 3 + 2) * 128 + row] = dot2;
+          ep_bar<NEPI>();
+          if (part == 0 && valid && io.rgb_out) {
 #pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                float z = __ldg(P.brgb + k) + dk[k];
+            for (int k = 0; k < 3; ++k) {
+              float z = __ldg(P.brgb + k);
 #pragma unroll
-                for (int pp = 1; pp < NPART; ++pp) z += xch[(pp * 3 + k) * 128 + row];
-                io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
-              }
+              for (int pp = 0; pp < NPART; ++pp) z += xch[(pp * 3 + k) * 128 + row];
+              io.rgb_out[3 * (size_t)slot + k] = 1.f / (1.f + __expf(-z));
             }
           }
         }

@@ -26,7 +26,7 @@ int prof_read(double* ms, long long* launches, double* points, int reset);
 // sampler.cu / composite.cu / background.cu
 int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field, const float* dirs,
                 const float* cam, int R, float* z_final, float* z_bg, int* trips_out, void* ws, size_t ws_bytes,
-                cudaStream_t st, const int* R_dev = nullptr);
+                cudaStream_t st, const int* R_dev = nullptr, const mp_sampler_rng_t* rng = nullptr, float* z_eik = nullptr);
 size_t sampler_ws_bytes(const mp_sampler_cfg_t& c, int R);
 struct CompositePersons {
   int P;

@@ -68,7 +68,8 @@ __global__ void tables_kernel(SamplerTables t, int E, int S, int X, int max_iter
 __global__ void sampler_init_kernel(const float* __restrict__ dirs, const float* __restrict__ cam, int R, float r,
                                     float near, int E, const float* __restrict__ tvals, float bound_coef,
                                     float* __restrict__ z, int zcap, float* __restrict__ beta,
-                                    float* __restrict__ far_out, SamplerState* st, const int* __restrict__ R_dev) {
+                                    float* __restrict__ far_out, SamplerState* st, const int* __restrict__ R_dev,
+                                    const float* __restrict__ t_rand) {
   int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (R_dev) R = min(R, *R_dev);     // device-side row count (hit list culled on the GPU, no host sync)
   if (ray >= R) return;
@@ -83,9 +84,15 @@ __global__ void sampler_init_kernel(const float* __restrict__ dirs, const float*
   far_out[ray] = far;
   float* zr = z + (size_t)ray * zcap;
   float prev = 0.f, sum = 0.f;
+  auto zu = [&](int j) { float t = tvals[j]; return near * (1.f - t) + far * t; };
   for (int j = 0; j < E; ++j) {
-    float t = tvals[j];
-    float zj = near * (1.f - t) + far * t;
+    float zj = zu(j);
+    if (t_rand) {
+      // training mode (model.training): stratified samples in the intervals between the midpoints   ray_sampler.py:32-40
+      float lower = (j == 0) ? zj : .5f * (zj + zu(j - 1));
+      float upper = (j == E - 1) ? zj : .5f * (zu(j + 1) + zj);
+      zj = lower + (upper - lower) * t_rand[(size_t)ray * E + j];
+    }
     zr[j] = zj;
     if (j > 0) {
       float dd = zj - prev;
@@ -213,7 +220,8 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
                                         const float* __restrict__ far, SamplerTables tab,
                                         float* __restrict__ z_out, float* __restrict__ sdf_out,
                                         int* __restrict__ pos_new, float* __restrict__ z_final,
-                                        SamplerState* st, int mmax, const int* __restrict__ R_dev) {
+                                        SamplerState* st, int mmax, const int* __restrict__ R_dev,
+                                        mp_sampler_rng_t rng, float* __restrict__ z_eik) {
   if (st->active[trip] == 0) return;
   if (R_dev) R = min(R, *R_dev);
   const bool cont = (st->not_converge[trip] != 0) && (trip + 1 < max_iters);
@@ -298,7 +306,9 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
   __syncwarp();
   // inverse CDF     :166-186
   const int N = cont ? E : S;
-  const float* u_tab = cont ? tab.u_E : tab.u_S;
+  // training mode draws the abscissae of the FINAL set at random (ray_sampler.py:171); every other set is linspace
+  const bool rnd = !cont && rng.u_final != nullptr;
+  const float* u_tab = cont ? tab.u_E : (rnd ? rng.u_final + (size_t)ray * S : tab.u_S);
   for (int j = lane; j < N; j += 32) {
     float u = u_tab[j];
     int inds = upper_bound_f(sc, M, u);          // searchsorted(right=True)
@@ -314,6 +324,30 @@ __global__ void sampler_resample_kernel(const float* __restrict__ z, const float
   __syncwarp();
   // the inverse CDF is monotone up to rounding; repair the (rare) 1-ulp inversions so that the
   // rank merge below equals torch.sort (:189, :209)
+  if (rnd) {
+    // final set, training mode: sort(cat([z_samples, near, far, z_vals[:, randperm(M)[:X]]]))   :194-209 — nothing is
+    // ordered (random abscissae, random extras), so the S+X+2 values are rank-sorted: rank = #smaller + #equal before
+    const int T = M / E - 1;                                   // trips before this one = row of the per-trip draws
+    const int* perm = rng.extra_perm + (size_t)T * max_iters * E;
+    const int n = S + X + 2;
+    float* vals = sp;                                          // sp | sc are contiguous: 2 * mmax >= S + X + 2 floats
+    for (int k = lane; k < n; k += 32)
+      vals[k] = (k < S) ? sn[k] : ((k == S) ? near : ((k == S + 1) ? far[ray] : sz[perm[k - S - 2]]));
+    __syncwarp();
+    float* zf = z_final + (size_t)ray * n;
+    for (int k = lane; k < n; k += 32) {
+      const float v = vals[k];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float w = vals[j];
+        rank += (w < v || (w == v && j < k)) ? 1 : 0;
+      }
+      zf[rank] = v;
+    }
+    __syncwarp();
+    if (lane == 0 && z_eik) z_eik[ray] = zf[rng.eik_idx[(size_t)T * R + ray]];       // :212-213
+    return;
+  }
   bool inv = false;
   for (int j = lane + 1; j < N; j += 32) inv |= (sn[j] < sn[j - 1]);
   if (__ballot_sync(0xffffffffu, inv)) {
@@ -363,9 +397,23 @@ __global__ void trips_kernel(const SamplerState* st, int max_iters, int* trips_o
   *trips_out = st->final_trip + 1;
 }
 
-__global__ void zbg_kernel(const float* tab, int R, float* z_bg) {
+// inverse-sphere depths: linspace(0,1,32) / bound (ray_sampler.py:215-218); in training mode the UniformSampler
+// jitters them too (:32-40), with the draws of the trip count the loop ended on
+__global__ void zbg_kernel(const float* tab, int R, float inv_bound, const float* __restrict__ t_rand_bg,
+                           const SamplerState* st, float* z_bg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < R * 32) z_bg[i] = tab[i & 31];
+  if (i >= R * 32) return;
+  if (!t_rand_bg) {
+    z_bg[i] = tab[i & 31];
+    return;
+  }
+  const int j = i & 31;
+  auto zu = [&](int k) { return linspace_at(0.f, 1.f, 32, k); };
+  const float zj = zu(j);
+  const float lower = (j == 0) ? zj : .5f * (zj + zu(j - 1));
+  const float upper = (j == 31) ? zj : .5f * (zu(j + 1) + zj);
+  const int T = st->final_trip < 0 ? 0 : st->final_trip;
+  z_bg[i] = (lower + (upper - lower) * t_rand_bg[(size_t)T * R * 32 + i]) * inv_bound;
 }
 
 struct SamplerWs {
@@ -402,7 +450,11 @@ static bool sampler_carve(Arena& a, const mp_sampler_cfg_t& c, int R, SamplerWs&
 // The whole Algorithm-1 loop for one person.  z_final [R, S+X+2].
 int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field, const float* dirs,
                 const float* cam, int R, float* z_final, float* z_bg, int* trips_out, void* ws, size_t ws_bytes,
-                cudaStream_t st, const int* R_dev) {
+                cudaStream_t st, const int* R_dev, const mp_sampler_rng_t* rng_in, float* z_eik) {
+  mp_sampler_rng_t rng;
+  memset(&rng, 0, sizeof(rng));
+  if (rng_in) rng = *rng_in;
+  const bool training = rng_in != nullptr;
   const int E = c.N_samples_eval, S = c.N_samples, X = c.N_samples_extra;
   MP_REQUIRE(E >= 2 && S >= 1 && X >= 0 && c.max_total_iters >= 1 && c.max_total_iters <= 8,
              "sampler: unsupported configuration (E=%d S=%d X=%d iters=%d)", E, S, X, c.max_total_iters);
@@ -419,7 +471,7 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
                                                  (float)(1.0 / c.scene_bounding_sphere), w.st);
   MP_LAUNCH_CHECK();
   sampler_init_kernel<<<div_up(R, 128), 128, 0, st>>>(dirs, cam, R, c.scene_bounding_sphere, c.near, E, w.tab.u_E,
-                                                      bound_coef, w.zA, zcap, w.beta, w.far, w.st, R_dev);
+                                                      bound_coef, w.zA, zcap, w.beta, w.far, w.st, R_dev, rng.t_rand);
   MP_LAUNCH_CHECK();
   float *zc = w.zA, *zn = w.zB, *sc = w.sA, *sn = w.sB;
   const int mmax = zcap;
@@ -438,7 +490,8 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
   for (int t = 0; t < c.max_total_iters; ++t) {
     const int M = (t + 1) * E;
     // SDF of the E new samples of every ray (multiply.py:137-151 under no_grad, ray_sampler.py:82-88)
-    MP_TRY(launch_deform_rays(body, dirs, cam, zc, zcap, t == 0 ? nullptr : w.pos_new, E, E, R, /*prune=*/1, sc,
+    // (training mode: the SDF callback does not clamp outliers, multiply.py:142 is eval-only -> exact far search)
+    MP_TRY(launch_deform_rays(body, dirs, cam, zc, zcap, t == 0 ? nullptr : w.pos_new, E, E, R, /*prune=*/training ? 0 : 1, sc,
                               zcap, w.xc_list, w.slot_list, &w.st->count[t], nullptr, &w.st->active[t], st, R_dev));
     MP_TRY(field_sdf_list(field, w.xc_list, w.slot_list, &w.st->count[t], R * E, sc, w.mlp_ws, w.mlp_ws_bytes, st));
     // shared memory per ray sized for THIS trip's list (M = (t+1) E entries; the final-set staging needs X + 2):
@@ -453,7 +506,7 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
     MP_LAUNCH_CHECK();
     sampler_resample_kernel<<<div_up(R, wr), wr * 32, wr * pw_r, st>>>(
         zc, sc, zcap, M, R, E, S, X, c.max_total_iters, c.add_tiny, c.near, t, w.beta, w.far, w.tab, zn, sn,
-        w.pos_new, z_final, w.st, stride, R_dev);
+        w.pos_new, z_final, w.st, stride, R_dev, rng, z_eik);
     MP_LAUNCH_CHECK();
     float* tz = zc; zc = zn; zn = tz;
     float* ts = sc; sc = sn; sn = ts;
@@ -463,7 +516,8 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
     MP_LAUNCH_CHECK();
   }
   if (z_bg) {
-    zbg_kernel<<<div_up(R * 32, 256), 256, 0, st>>>(w.tab.z_bg, R, z_bg);
+    zbg_kernel<<<div_up(R * 32, 256), 256, 0, st>>>(w.tab.z_bg, R, (float)(1.0 / c.scene_bounding_sphere), rng.t_rand_bg,
+                                                    w.st, z_bg);
     MP_LAUNCH_CHECK();
   }
   return 0;
@@ -491,6 +545,17 @@ int mp_sample_rays(const mp_sampler_cfg_t* cfg, mp_body_t* body, mp_net_t* field
   MP_REQUIRE(cfg && body && field && ray_dirs && cam_loc && z_vals, "mp_sample_rays: null argument");
   MP_REQUIRE(body->b.tfs, "mp_sample_rays: body has no pose (call mp_body_set_pose)");
   return mp::sample_rays(*cfg, body->b, field->f, ray_dirs, cam_loc, R, z_vals, z_bg, trips_out, workspace,
-                         workspace_bytes, (cudaStream_t)stream, nullptr);
+                         workspace_bytes, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
+int mp_sample_rays_train(const mp_sampler_cfg_t* cfg, mp_body_t* body, mp_net_t* field, const float* ray_dirs,
+                         const float* cam_loc, int R, const mp_sampler_rng_t* rng, float* z_vals, float* z_bg,
+                         float* z_eik, int* trips_out, void* workspace, size_t workspace_bytes, void* stream) {
+  MP_REQUIRE(cfg && body && field && ray_dirs && cam_loc && z_vals && rng, "mp_sample_rays_train: null argument");
+  MP_REQUIRE(rng->t_rand && rng->u_final && rng->eik_idx && (cfg->N_samples_extra == 0 || rng->extra_perm),
+             "mp_sample_rays_train: incomplete random draws");
+  MP_REQUIRE(body->b.tfs, "mp_sample_rays_train: body has no pose (call mp_body_set_pose)");
+  return mp::sample_rays(*cfg, body->b, field->f, ray_dirs, cam_loc, R, z_vals, z_bg, trips_out, workspace,
+                         workspace_bytes, (cudaStream_t)stream, nullptr, rng, z_eik);
 }
 }

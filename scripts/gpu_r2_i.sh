@@ -1,0 +1,16 @@
+cd $GRAFT_REPO_ROOT
+export PYTHONPATH=$GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+run() { v=$1; prec=$2;
+  L=$GRAFT_REPO_ROOT/multiply_b200/_variants/lib_$v.so
+  MP_LIB=$L timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --precision $prec 2>&1 | tail -1 > gpurun_out/bench_var_${v}_$prec.json
+  python -c "
+import json,sys
+try:
+  d=json.load(open('gpurun_out/bench_var_${v}_$prec.json')); r=d['roofline']
+  print('$v $prec', 'value',round(d['value']),'kernel_ms',round(r['kernel_ms_per_step'],3),'frac',round(r['frac'],4),'serial',round(r['ms_per_step_single_stream'],3), 'e2e', round(d['e2e']['value']))
+except Exception as e: print('$v', 'FAILED', e, open('gpurun_out/bench_var_${v}_$prec.json').read()[-300:])"
+}
+run vA parity; run vD parity; run vD colour1; run vD throughput
+MP_LIB=$GRAFT_REPO_ROOT/multiply_b200/_variants/lib_vD.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
+echo "=== trace vD"; MP_LIB=$GRAFT_REPO_ROOT/multiply_b200/_variants/lib_vD.so timeout 300 python scripts/gpu_trace.py 2>&1 | tail -34 | head -24

@@ -159,6 +159,74 @@ def test_query_oc_and_dense_grid(golden_dir):
     assert torch.equal(dense.reshape(-1), occ[:, 0])
 
 
+def test_sampler_training_mode(golden_dir):
+    """f1, forward half: ErrorBoundSampler.get_z_vals with model.training (stratified start samples, random final
+    abscissae, randperm extras, eikonal pick, jittered inverse-sphere depths, no outlier clamp in the SDF callback)
+    against the reference's own sampler in training mode — (a) with the recorded random draws passed in
+    (mp_sample_rays_train), (b) through the mirror with the same torch.manual_seed, which replays the reference's
+    random stream."""
+    import os
+    import ctypes as C
+    from multiply_b200 import engine, _lib as L
+    from multiply_b200.model.ray_sampler import ErrorBoundSampler
+    from multiply_b200.model import rend_util
+    engine.set_engine("tc")
+    g = np.load(os.path.join(golden_dir, "sampler_train.npz"))
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inputs = S.make_rays(sc, 40, seed=21, region="boxes")
+    dirs, cam = rend_util.get_camera_params_host(inputs["uv"], inputs["pose"], inputs["intrinsics"])
+    idx = torch.from_numpy(g["hits"])
+    d, o = dirs[idx].cuda(), cam[idx].cuda()
+    R = idx.numel()
+    p0 = sc["persons"][0]
+    m = _build(sc)
+    cfg = sc["cfg"]
+    smp = ErrorBoundSampler(3.0, cfg["near"], cfg["N_samples"], cfg["N_samples_eval"], cfg["N_samples_extra"], cfg["eps"],
+                            cfg["beta_iters"], cfg["max_total_iters"], inverse_sphere_bg=True, add_tiny=cfg["add_tiny"])
+    T, E = cfg["max_total_iters"], cfg["N_samples_eval"]
+    trips_ref = g["extra_perm"].shape[0] // E
+    rng = smp.draw_training_rng(R)
+    rng.pop("states")
+    rng["t_rand"], rng["u_final"] = torch.from_numpy(g["t_rand"]), torch.from_numpy(g["u_final"])
+    rng["extra_perm"][trips_ref - 1, :trips_ref * E] = torch.from_numpy(g["extra_perm"]).to(torch.int32)
+    rng["eik_idx"][trips_ref - 1] = torch.from_numpy(g["eik_idx"]).to(torch.int32)
+    rng["t_rand_bg"][trips_ref - 1] = torch.from_numpy(g["t_rand_bg"])
+
+    def check(z, z_bg, z_eik, trips):
+        assert int(trips.item()) == trips_ref
+        assert float(np.abs(z_bg.cpu().numpy() - g["z_bg"]).max()) < 1e-6
+        dz = np.abs(z.cpu().numpy() - g["z_vals"])
+        assert np.median(dz) < 1e-5 and dz.max() < 5e-3         # coarse 16/32/8 sampler: see test_forward_golden_coarse
+        assert float(np.abs(z_eik.cpu().numpy() - g["z_eik"]).max()) < 5e-3
+
+    m.train()
+    try:
+        # (a) recorded draws
+        lib = L.lib()
+        c = engine.sampler_cfg(smp.cfg, float(m.density.beta.detach()), float(m.density.beta_min))
+        body = m.deformer_list[0].body(d.device)
+        body.set_pose(p0["verts_p"].cuda(), p0["tfs"].cuda())
+        field = m.field_list[0]
+        field.set_cond(p0["cond"].cuda())
+        z = torch.empty(R, cfg["N_samples"] + cfg["N_samples_extra"] + 2, device="cuda")
+        z_bg = torch.empty(R, 32, device="cuda")
+        trips = torch.zeros(1, dtype=torch.int32, device="cuda")
+        smp._ws = torch.empty(lib.mp_sampler_workspace_bytes(C.byref(c), R), dtype=torch.uint8, device="cuda")
+        (z, z_bg), z_eik = smp._get_z_vals_training(lib, c, body, field, d.contiguous(), o.contiguous(), R, z, z_bg, trips,
+                                                    d.device, rng=rng)
+        torch.cuda.synchronize()
+        check(z, z_bg, z_eik, trips)
+        # (b) the mirror draws the reference's random stream itself
+        torch.manual_seed(1234)
+        (z2, z_bg2), z_eik2 = smp.get_z_vals(d, o, m, {"smpl": p0["cond"].cuda()}, p0["tfs"][None].cuda(), False,
+                                              p0["verts_p"][None].cuda(), 0)
+        torch.cuda.synchronize()
+        check(z2, z_bg2, z_eik2, smp.last_trips)
+        assert torch.equal(z2, z) and torch.equal(z_eik2, z_eik)
+    finally:
+        m.eval()
+
+
 def test_load_reference_checkpoint_keys():
     """A Lightning checkpoint of the reference (keys 'model.*', plus smpl_server_list / deformer_list buffers and
     MultiplyModel's body_model_list, train.py:16-22) loads through load_reference_checkpoint with strict=True."""
