@@ -303,6 +303,11 @@ def extras_full_frame(dev, rank, world):
     res, chunk = 512, 16384
     sc, model, smpl_in = S.make_smpl_scene(P=3, S=256, seed=42, device=dev)
     frame = S.grid_rays(res=res)
+    # the synthetic camera looks down the world z axis from (0, 0, 2.5): the ray of the central pixel passes through the
+    # origin, where depth2pts_outside's rotation axis cross(o, p_sphere) is 0/0 — NaN in the reference too
+    # (multiply.py:712-714).  Shift the camera a hair so that the frame statistic below is finite.
+    frame["pose"] = frame["pose"].clone()
+    frame["pose"][0, 0, 3] = 0.013
     inputs = {k: v.to(dev) for k, v in dict(frame, **smpl_in).items()}
     chunks = idr_utils.split_input(inputs, res * res, n_pixels=chunk)
     mine = chunks[rank::world]

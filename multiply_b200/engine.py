@@ -342,7 +342,7 @@ class Renderer:
         L.check(lib.mp_render_rays(C.byref(sc), uv.data_ptr(), pose.data_ptr(), K.data_ptr(), R, C.byref(out),
                                    self._ws.data_ptr(), self._ws.numel(), L.stream_ptr()), "mp_render_rays")
         self._keep = (uv, pose, K, hits)
-        if check or debug:
+        if check:
             self.check_status()
         res.update(dbg)
         return res

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r2.csv \
    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_bench_stdout.log 2>&1
 # full capture of the dominant kernel: the launches of one warm step (sdf-only trips, both shade launches, background)
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 13 -c 8 -o gpurun_out/prof_tc_r2 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 13 -c 13 -o gpurun_out/prof_tc_r2 \
    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_full_stdout.log 2>&1
 # memcheck of smoke()
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/sanitizer_r2.log 2>&1

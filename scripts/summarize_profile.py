@@ -14,7 +14,8 @@ for r in csv.DictReader(lines):
     if r.get("Metric Name") == "gpu__time_duration.sum":
         rows.append((int(r["ID"]), r["Kernel Name"].split("(")[0], float(r["Metric Value"].replace(",", ""))))
 idx = [i for i, r in enumerate(rows) if "camera_rays" in r[1]]
-s, e = idx[1], idx[2]            # second step of the first timed loop (warm)
+s = idx[1]                       # second resident-input step (warm)
+e = next(i for i in range(s, len(rows)) if "final_compose" in rows[i][1]) + 1
 agg = collections.OrderedDict()
 tot = 0.0
 for r in rows[s:e]:
@@ -50,9 +51,9 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_p
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 with open(f"{out_dir}/{tag}_tc_kernel.md", "w") as f:
     f.write(f"# ncu --set full capture of `tc_chain_kernel` ({tag})\n\n")
-    f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 5 -c 8 python bench.py "
-            "--steps 1 --warmup 1 --no-cpu-baseline`.  Launch order per step: person 0: sdf-only x5 (trips; inactive ones "
-            "exit), shade; person 1: same; background.\n\n")
+    f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 13 -c 13 python bench.py "
+            "--steps 1 --warmup 1 --no-cpu-baseline --no-extras`.  Launch order per step: background; person 0: sdf-only x5 "
+            "(sampler trips; inactive ones exit), shade; person 1: same.\n\n")
     for r in rr[2:]:
         t = r[ix["gpu__time_duration.sum"]]
         f.write(f"## launch id {r[ix['ID']]}  ({t} {units[ix['gpu__time_duration.sum']]})\n\n| metric | value | unit |\n|---|---:|---|\n")
