@@ -363,6 +363,28 @@ def extras_sdf_grid(dev):
             "batch_10k_points_per_s": 100 * 10000 / (e0.elapsed_time(e1) / 1000.0)}
 
 
+def extras_precision(timer, r, d_inp, d_hits, R, steps, oracle_check):
+    """The tcgen05 precision modes side by side (mp_set_precision): `parity` (three split terms everywhere, the headline),
+    `colour1` (single-term colour layers), `throughput` (one fp16 term everywhere): rays/s of the resident-input step and,
+    when the oracle sample is available, the measured L-inf of each mode against it."""
+    from multiply_b200 import engine
+    out = {}
+    try:
+        for mode in ("parity", "colour1", "throughput"):
+            engine.set_precision(mode)
+            ms, _ = timer.run(lambda: r.render(d_inp, d_hits), steps, 3)
+            rec = {"rays_per_s": R * steps / (ms / 1000.0), "ms_per_step": ms / steps}
+            if oracle_check is not None:
+                rec.update(oracle_check())
+            out[mode] = rec
+    finally:
+        engine.set_precision("parity")
+    out["terms"] = {"parity": "A_hi.W_hi + A_lo.W_hi + A_hi.W_lo in every layer (fp16 hi/lo operands, fp32 accumulate)",
+                    "colour1": "colour layers A_hi.W_hi only; SDF net and reverse sweep as parity",
+                    "throughput": "A_hi.W_hi in every layer (plain fp16 tensor-core inference; outside the 1e-4 gate)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -575,6 +597,19 @@ def main():
             parity.update({"rgb_linf_vs_oracle": linf(og["rgb_values"], ref["rgb_values"]),
                            "normal_linf_vs_oracle": linf(og["normal_values"], ref["normal_values"]),
                            "acc_linf_vs_oracle": linf(og["acc_map"], ref["acc_map"]), "rays": n_sample})
+        if not args.no_extras and world == 1:
+            chk = None
+            if not args.no_cpu_baseline:
+                def chk():
+                    og2 = r.render(sub, shits, debug=True)
+                    torch.cuda.synchronize()
+                    return {"rgb_linf_vs_oracle": linf(og2["rgb_values"], ref["rgb_values"]),
+                            "normal_linf_vs_oracle": linf(og2["normal_values"], ref["normal_values"]),
+                            "acc_linf_vs_oracle": linf(og2["acc_map"], ref["acc_map"])}
+            try:
+                extras["precision_modes"] = extras_precision(timer, r, d_inp, d_hits, R, max(3, min(args.steps, 10)), chk)
+            except Exception as e:
+                extras["precision_modes"] = {"error": "%s: %s" % (type(e).__name__, e)}
         line["parity"] = parity
         line["extras"] = extras
         print(json.dumps(line))

@@ -48,6 +48,7 @@ class Multiply(nn.Module):
         self.ray_sampler = ErrorBoundSampler(self.sdf_bounding_sphere, inverse_sphere_bg=True, **rs)
         self._renderer = None
         self._key = None
+        self._side = {}
         self.output_buffers = None      # optional dict of preallocated output tensors (parallel.PixelBuffer.views)
         # the packed kernels are built for the shipped network shapes (confs/model/*.yaml:12,17-58): fail loudly otherwise
         fe = _get(opt, "dim_frame_encoding")
@@ -126,6 +127,12 @@ class Multiply(nn.Module):
         feature = output[:, 1:]
         return sdf, x_c, feature
 
+    def _side_streams(self, dev, n):
+        key = str(dev)
+        if len(self._side.get(key, [])) < n:
+            self._side[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        return self._side[key][:n]
+
     # ---- Multiply.forward, eval branch -------------------------------------------------------
     def forward(self, input, id=-1, cond_zero_shit=False, canonical_pose=False):
         """multiply.py:174-598, eval branch.  ``id``: render only that person (``person_list = [id]``, :244-247: its
@@ -144,27 +151,68 @@ class Multiply(nn.Module):
         P = smpl_trans.shape[1]
         if id != -1 and not (0 <= int(id) < P):
             raise IndexError("person id %r out of range (num_person = %d)" % (id, P))
-        persons = []
-        for i in range(P):
+        person_list = list(range(P)) if id == -1 else [int(id)]            # multiply.py:244-247
+        hits_in = input.get("index_ray_box_list")
+        if hits_in is not None and len(hits_in) == P and len(person_list) != P:
+            hits_in = [hits_in[i] for i in person_list]
+        need_rays = hits_in is None
+        if need_rays:
+            dirs, cam = rend_util.get_camera_params(input["uv"], input["pose"], input["intrinsics"])
+            dirs = dirs[0]
+            cam = cam.expand(dirs.shape[0], 3).contiguous()
+        # Per-person preparation — SMPL server, pose conditioning, posed-grid rebuild, culling — is a chain of small
+        # single-CTA kernels (multiply.py:196-214, :256-263, :270).  The persons' chains are independent, so each runs on
+        # its own side stream and the caller's stream waits for all of them before the render: the chains overlap
+        # instead of queueing (pure stream plumbing; every kernel is the library's).
+        main = torch.cuda.current_stream(dev)
+        side = self._side_streams(dev, len(person_list)) if len(person_list) > 1 else [main] * len(person_list)
+        start = torch.cuda.Event()
+        start.record(main)
+        persons = {}
+        hits = []
+        first_build = self._renderer is None
+        if first_build:
+            side = [main] * len(person_list)        # the renderer (weights) is packed on the caller's stream first
+
+        def smpl_out(i):
             if canonical_pose:                                             # multiply.py:196-201
                 cpose = torch.zeros_like(smpl_pose[:, i])
                 cpose[0, 5] = np.pi / 6
                 cpose[0, 8] = -np.pi / 6
-                out = self.smpl_server_list[i](scale[:, i], torch.zeros_like(smpl_trans[:, i]), cpose, smpl_shape[:, i])
-            else:
-                out = self.smpl_server_list[i](scale[:, i], smpl_trans[:, i], smpl_pose[:, i], smpl_shape[:, i])
-            cond_pose = smpl_pose[:, i, 3:] / np.pi                        # multiply.py:270
-            persons.append(dict(verts_p=out["smpl_verts"].reshape(-1, 3), tfs=out["smpl_tfs"].reshape(24, 4, 4),
-                                cond=cond_pose))
-        if self._renderer is None:
-            full = [self._person_dict(i, dict(smpl_verts=persons[i]["verts_p"], smpl_tfs=persons[i]["tfs"]),
-                                      persons[i]["cond"]) for i in range(P)]
+                return self.smpl_server_list[i](scale[:, i], torch.zeros_like(smpl_trans[:, i]), cpose, smpl_shape[:, i])
+            return self.smpl_server_list[i](scale[:, i], smpl_trans[:, i], smpl_pose[:, i], smpl_shape[:, i])
+
+        if first_build:
+            full = []
+            for i in range(P):
+                out = smpl_out(i)
+                full.append(self._person_dict(i, out, smpl_pose[:, i, 3:] / np.pi))
             r = self._ensure_renderer(dev, full)
         else:
             r = self._ensure_renderer(dev)
-        person_list = list(range(P)) if id == -1 else [int(id)]            # multiply.py:244-247
-        for i in person_list:
-            r.update_person(i, persons[i])
+        done = []
+        for k, i in enumerate(person_list):
+            st = side[k]
+            with torch.cuda.stream(st):
+                if st is not main:
+                    st.wait_event(start)
+                out = smpl_out(i)
+                pd = dict(verts_p=out["smpl_verts"].reshape(-1, 3), tfs=out["smpl_tfs"].reshape(24, 4, 4),
+                          cond=smpl_pose[:, i, 3:] / np.pi)                # multiply.py:270
+                persons[i] = pd
+                r.update_person(i, pd)
+                if need_rays:
+                    # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2 — box, test, ordered
+                    # compaction and the empty-list rule all on the device; the count stays there
+                    hits.append(engine.ray_aabb_hits(cam, dirs, pd["verts_p"], 1.2))
+                if st is not main:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    done.append(ev)
+        for ev in done:
+            main.wait_event(ev)
+        if not need_rays:
+            hits = hits_in
         if "image_id" in input:
             frame = self.frame_latent_encoder(input["image_id"])          # multiply.py:407-410
         elif input.get("idx") is not None:
@@ -173,16 +221,6 @@ class Multiply(nn.Module):
             frame = None
         if frame is not None and r.bg is not None:
             r.bg.set_cond(frame.detach())
-        hits = input.get("index_ray_box_list")
-        if hits is None:
-            # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2 — box, test, ordered compaction and
-            # the empty-list rule all on the device; the count stays there
-            dirs, cam = rend_util.get_camera_params(input["uv"], input["pose"], input["intrinsics"])
-            dirs = dirs[0]
-            cam = cam.expand(dirs.shape[0], 3).contiguous()
-            hits = [engine.ray_aabb_hits(cam, dirs, persons[i]["verts_p"], 1.2) for i in person_list]
-        elif len(hits) == P and len(person_list) != P:
-            hits = [hits[i] for i in person_list]
         bg_saved = r.bg
         if frame is None:
             r.bg = None                                                    # white background, multiply.py:540-541
