@@ -470,6 +470,26 @@ def main():
     torch.cuda.synchronize()
     trips = o["trips"].cpu().tolist()
 
+    # ---- the same resident-input step replayed from a CUDA graph (one graph launch instead of ~60 kernel launches)
+    graph_rec = None
+    try:
+        gr = engine.GraphedRender(r, d_inp, d_hits)
+
+        def step_graph():
+            gr.replay()
+            if world > 1:
+                buf.flat.copy_(torch.cat([gr.out[k].reshape(-1) for k in parallel.PIXEL_KEYS]))
+                dist.all_gather_into_tensor(gathered, buf.flat)
+
+        ms_graph, _ = timer.run(step_graph, args.steps, args.warmup)
+        torch.cuda.synchronize()
+        graph_rec = {"rays_per_s": R * world * args.steps / (ms_graph / 1000.0), "ms_per_step": ms_graph / args.steps,
+                     "bit_equal_to_eager": all(torch.equal(gr.out[k], o[k]) for k in parallel.PIXEL_KEYS),
+                     "what": "engine.GraphedRender: mp_render_rays (63 launches, fork/join over 3 streams) captured once, "
+                             "replayed per step; inputs resident"}
+    except Exception as e:
+        graph_rec = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- parity at every N: the gathered frame against the same rays rendered on ONE GPU, and the drop-in call against
     # the resident-input renderer on this rank's shard
     parity = {}
@@ -610,6 +630,7 @@ def main():
                 extras["precision_modes"] = extras_precision(timer, r, d_inp, d_hits, R, max(3, min(args.steps, 10)), chk)
             except Exception as e:
                 extras["precision_modes"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        extras["cuda_graph"] = graph_rec
         line["parity"] = parity
         line["extras"] = extras
         print(json.dumps(line))

@@ -348,6 +348,36 @@ class Renderer:
         return res
 
 
+class GraphedRender:
+    """One eval forward captured in a CUDA graph and replayed: the ~60 kernel launches, memsets and the stream fork/join
+    of mp_render_rays become a single graph launch (the sampler trips and the MLP tile counts are read from device
+    memory, so nothing in the launch configuration depends on the data).  The input tensors are static device buffers —
+    write new rays / camera into ``uv`` / ``pose`` / ``intrinsics`` (and new hit ids / counts into the hit-list
+    tensors given at capture) and ``replay()``; poses are updated as usual through ``Renderer.update_person``."""
+
+    def __init__(self, renderer, inputs, hit_lists, persons=None):
+        self.r = renderer
+        dev = renderer.device
+        self.inputs = {k: _dev(inputs[k], dev).clone() for k in ("uv", "pose", "intrinsics")}
+        self.hits = [tuple(t.to(dev) for t in h) if isinstance(h, (tuple, list)) else h.to(dev).clone() for h in hit_lists]
+        self.persons = persons
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                      # warm-up outside the capture: lazy resources, workspace size
+                    renderer.render(self.inputs, self.hits, persons=persons)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = renderer.render(self.inputs, self.hits, persons=persons)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 def ray_aabb_hits(cam_loc, ray_dirs, verts, inflate=1.2):
     """Device-side culling against the x`inflate` axis-aligned box of `verts` [V,3] (multiply.py:208-214 uses trimesh's
     oriented box): returns (ids [R] int64, count [1] int32), both on the device, the list already
