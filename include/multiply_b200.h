@@ -296,6 +296,16 @@ int mp_background(mp_net_t* bg_field, const float* ray_dirs, const float* cam_lo
 /* ------------------------------------------------------------------------------------------
  * the fused entry used by Multiply.forward (multiply.py:174-598, eval branch)
  * ---------------------------------------------------------------------------------------- */
+/* Training-mode forward VALUES (multiply.py:174-598 with self.training, shipped loss weights, current_epoch >= 250):
+ * stochastic sampling per person (mp_sampler_rng_t), no outlier clamp in the SDF callback or the main pass
+ * (multiply.py:142 is eval-only), jittered inverse-sphere depths of the background pass (the second
+ * inverse_sphere_sampler.get_z_vals call, :482).  Gradients are NOT produced. */
+typedef struct {
+  const mp_sampler_rng_t* rng[MP_MAX_PERSONS]; /* host structs of device pointers, one per person */
+  float* z_eik[MP_MAX_PERSONS];                /* [R_p] z_samples_eik out, or NULL */
+  const float* t_rand_bg;                      /* [R,32] torch.rand of the background's UniformSampler, or NULL */
+} mp_train_t;
+
 typedef struct {
   mp_sampler_cfg_t sampler;
   int P;
@@ -308,6 +318,7 @@ typedef struct {
    * when hit_count_dev[p] != NULL, hit_count[p] is the CAPACITY of hit_index[p] (normally R) and the number of valid
    * rows is read on the device by every kernel of person p's branch.  NULL -> hit_count[p] is exact. */
   const int* hit_count_dev[MP_MAX_PERSONS];
+  const mp_train_t* train;                  /* NULL: eval mode */
 } mp_scene_t;
 
 typedef struct {

@@ -56,12 +56,17 @@ class PersonSamples(C.Structure):
                 ("rgb", C.c_void_p), ("normal", C.c_void_p)]
 
 
+class Train(C.Structure):
+    _fields_ = [("rng", C.POINTER(SamplerRng) * MP_MAX_PERSONS), ("z_eik", C.c_void_p * MP_MAX_PERSONS),
+                ("t_rand_bg", C.c_void_p)]
+
+
 class Scene(C.Structure):
     _fields_ = [("sampler", SamplerCfg), ("P", C.c_int),
                 ("body", C.c_void_p * MP_MAX_PERSONS), ("field", C.c_void_p * MP_MAX_PERSONS),
                 ("bg_field", C.c_void_p),
                 ("hit_index", C.c_void_p * MP_MAX_PERSONS), ("hit_count", C.c_int * MP_MAX_PERSONS),
-                ("hit_count_dev", C.c_void_p * MP_MAX_PERSONS)]
+                ("hit_count_dev", C.c_void_p * MP_MAX_PERSONS), ("train", C.POINTER(Train))]
 
 
 class RenderOut(C.Structure):

@@ -18,12 +18,25 @@ __device__ __forceinline__ float bg_linspace32(int i) {
 }
 
 // one thread per (ray, sample): depth = flip(linspace(0,1,32) / bound)[j] ; pts = depth2pts_outside(o, d, depth)
+// inverse-sphere depth k of ray r: linspace(0,1,32)[k] / bound (ray_sampler.py:215-218); with t_rand (training mode:
+// the UniformSampler of the inverse sphere sees model.training, ray_sampler.py:32-40) stratified between the midpoints
+__device__ __forceinline__ float bg_depth(int r, int k, float inv_bound, const float* __restrict__ t_rand) {
+  float zk = bg_linspace32(k);
+  if (t_rand) {
+    float lower = (k == 0) ? zk : .5f * (zk + bg_linspace32(k - 1));
+    float upper = (k == 31) ? zk : .5f * (bg_linspace32(k + 1) + zk);
+    zk = lower + (upper - lower) * t_rand[(size_t)r * 32 + k];
+  }
+  return zk * inv_bound;
+}
+
 __global__ void bg_points_kernel(const float* __restrict__ dirs, const float* __restrict__ cam, int R, float bound,
-                                 float inv_bound, float* __restrict__ pts, float* __restrict__ dirs_out) {
+                                 float inv_bound, float* __restrict__ pts, float* __restrict__ dirs_out,
+                                 const float* __restrict__ t_rand) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * 32) return;
   int r = idx >> 5, j = idx & 31;
-  float depth = bg_linspace32(31 - j) * inv_bound;     // torch.flip(z_vals_bg)   multiply.py:516
+  float depth = bg_depth(r, 31 - j, inv_bound, t_rand);     // torch.flip(z_vals_bg)   multiply.py:516
   const float* o = cam + 3 * r;
   const float* d = dirs + 3 * r;
   float odd = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
@@ -60,13 +73,13 @@ __global__ void bg_points_kernel(const float* __restrict__ dirs, const float* __
 
 // one warp per ray, lane = sample     multiply.py:682-696, :539
 __global__ void bg_composite_kernel(const float* __restrict__ sdf, const float* __restrict__ rgb, int R,
-                                    float inv_bound, float* __restrict__ out) {
+                                    float inv_bound, float* __restrict__ out, const float* __restrict__ t_rand) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= R) return;
   size_t i = (size_t)w * 32 + lane;
   float dens = fabsf(sdf[i]);
-  float zc = bg_linspace32(31 - lane) * inv_bound;
-  float zn = (lane < 31) ? bg_linspace32(30 - lane) * inv_bound : 0.f;
+  float zc = bg_depth(w, 31 - lane, inv_bound, t_rand);
+  float zn = (lane < 31) ? bg_depth(w, 30 - lane, inv_bound, t_rand) : 0.f;
   float dist = (lane < 31) ? (zc - zn) : 1e10f;
   float fe = dist * dens;
   float T = expf(-warp_scan_excl(fe, lane));
@@ -84,7 +97,7 @@ size_t bg_ws_bytes(int R) {
 }
 
 int render_background(const Field& f, const float* dirs, const float* cam, int R, float bound, float* bg_rgb,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      void* ws, size_t ws_bytes, cudaStream_t st, const float* t_rand) {
   if (R <= 0) return 0;
   Arena a(ws, ws_bytes);
   int N = R * 32;
@@ -96,10 +109,10 @@ int render_background(const Field& f, const float* dirs, const float* cam, int R
   void* mws = a.take<char>(mb);
   MP_REQUIRE(a.ok, "background: workspace too small (%zu needed, %zu given)", a.off, ws_bytes);
   float inv_bound = (float)(1.0 / bound);
-  bg_points_kernel<<<div_up(N, 256), 256, 0, st>>>(dirs, cam, R, bound, inv_bound, pts, dexp);
+  bg_points_kernel<<<div_up(N, 256), 256, 0, st>>>(dirs, cam, R, bound, inv_bound, pts, dexp, t_rand);
   MP_LAUNCH_CHECK();
   MP_TRY(field_bg(f, pts, dexp, N, sdf, rgb, mws, mb, st));
-  bg_composite_kernel<<<div_up(N, 256), 256, 0, st>>>(sdf, rgb, R, inv_bound, bg_rgb);
+  bg_composite_kernel<<<div_up(N, 256), 256, 0, st>>>(sdf, rgb, R, inv_bound, bg_rgb, t_rand);
   MP_LAUNCH_CHECK();
   return 0;
 }
@@ -113,6 +126,6 @@ int mp_background(mp_net_t* bg_field, const float* ray_dirs, const float* cam_lo
                   void* workspace, size_t workspace_bytes, void* stream) {
   MP_REQUIRE(bg_field && ray_dirs && cam_loc && bg_rgb, "mp_background: null argument");
   return mp::render_background(bg_field->f, ray_dirs, cam_loc, R, bound_r, bg_rgb, workspace, workspace_bytes,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, nullptr);
 }
 }

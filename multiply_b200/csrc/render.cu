@@ -43,7 +43,7 @@ int launch_row_of_ray(const int64_t* idx, int n_rows, int R, int* row_of_ray, cu
 int launch_final_compose(const float* fg, const float* bgT, const float* bg, int R, float* rgb, float* fg_out,
                          cudaStream_t st);
 int render_background(const Field& f, const float* dirs, const float* cam, int R, float bound, float* bg_rgb,
-                      void* ws, size_t ws_bytes, cudaStream_t st);
+                      void* ws, size_t ws_bytes, cudaStream_t st, const float* t_rand = nullptr);
 size_t bg_ws_bytes(int R);
 
 static size_t engine_ws_bytes(int N) {
@@ -361,9 +361,13 @@ static int render_person(const mp_scene_t* scene, int p, int R, const RenderWs& 
   const PersonBufs& b = w.pb[p];
   gather_rays_kernel<<<div_up(Rp, 256), 256, 0, st>>>(w.dirs, w.cam, scene->hit_index[p], Rp, Rp_dev, b.dirs, b.cam);
   MP_LAUNCH_CHECK();
-  // ray_sampler.get_z_vals (multiply.py:285-289)
+  // ray_sampler.get_z_vals (multiply.py:285-289); training mode (scene->train): stochastic, no outlier clamp anywhere
+  const mp_train_t* tr = scene->train;
+  MP_REQUIRE(!tr || (tr->rng[p] && !Rp_dev), "mp_render_rays: training mode needs the random draws of person %d and "
+                                              "host-side hit counts", p);
+  if (tr) prune = 0;
   MP_TRY(sample_rays(c, body, field, b.dirs, b.cam, Rp, b.z, nullptr, out->trips ? out->trips + p : nullptr, w.sub[p],
-                     w.sub_bytes, st, Rp_dev));
+                     w.sub_bytes, st, Rp_dev, tr ? tr->rng[p] : nullptr, tr ? tr->z_eik[p] : nullptr));
   // main pass (multiply.py:295-308, 403-404): deform, SDF, normals, colour
   MP_CHECK_CUDA(cudaMemsetAsync(b.count, 0, sizeof(int), st));
   MP_CHECK_CUDA(cudaMemsetAsync(b.rgb, 0, (size_t)Rp * n * 3 * sizeof(float), st));
@@ -374,7 +378,7 @@ static int render_person(const mp_scene_t* scene, int p, int R, const RenderWs& 
   if (pre_shade) MP_CHECK_CUDA(cudaEventRecord(pre_shade, st));
   MP_TRY(field_shade_list(field, b.xc_list, b.slot_list, b.count, Rp * n, b.jinv, b.sdf, b.rgb, b.nrm, nullptr,
                           nullptr, w.sub[p], w.sub_bytes, st));
-  if (!prune) {
+  if (!prune && !tr) {     // (multiply.py:142-143 is eval-only)
     force_outlier_sdf_kernel<<<div_up(Rp * n, 256), 256, 0, st>>>(b.outl, Rp * n, b.sdf);
     MP_LAUNCH_CHECK();
   }
@@ -475,7 +479,7 @@ int mp_render_rays(const mp_scene_t* scene, const float* uv, const float* pose, 
     }
     if (rc == 0)
       rc = render_background(scene->bg_field->f, w.dirs, w.cam, R, c.scene_bounding_sphere, w.bg, w.sub[scene->P],
-                             w.sub_bytes, sb);
+                             w.sub_bytes, sb, scene->train ? scene->train->t_rand_bg : nullptr);
     bg = w.bg;
   }
   if (fork) {

@@ -258,7 +258,7 @@ class Renderer:
             raise RuntimeError("BOUNDING SPHERE PROBLEM! (a camera ray misses the r=%g scene sphere)"
                                % self.cfg["scene_bounding_sphere"])
 
-    def render(self, inputs, hit_lists, debug=False, persons=None, check=False, out=None):
+    def render(self, inputs, hit_lists, debug=False, persons=None, check=False, out=None, train=None):
         """inputs: uv [1,R,2], pose [1,4,4], intrinsics [1,4,4] (CUDA or CPU tensors);
         hit_lists: per rendered person either an int64 tensor of ray ids (empty -> ray 0, multiply.py:262-263) or a
         pair (ids [R] int64 on the device, count [1] int32 on the device) as produced by ``ray_aabb_hits`` — the
@@ -266,12 +266,15 @@ class Renderer:
         persons: indices of the persons to render (default: all; ``Multiply.forward(input, id=p)`` passes [p],
         multiply.py:244-247) — ``acc_person_list`` has one column per rendered person;
         check: read the bounding-sphere status flag after the call (synchronises) and raise like the reference;
-        out: optional dict of preallocated contiguous output tensors (e.g. ``parallel.PixelBuffer.views``).
+        out: optional dict of preallocated contiguous output tensors (e.g. ``parallel.PixelBuffer.views``);
+        train: training-mode VALUES (mp_train_t): dict(rng=[per rendered person the tabled draws of
+        ``ErrorBoundSampler.draw_training_rng``], t_rand_bg=[R,32] or None) — stochastic sampling, no outlier clamp,
+        jittered background depths; adds ``z_eik_{k}`` [R_k] per person.  No gradients.
         Returns the eval output dict of Multiply.forward (multiply.py:589-598)."""
         with torch.cuda.device(self.device):
-            return self._render(inputs, hit_lists, debug, persons, check, out)
+            return self._render(inputs, hit_lists, debug, persons, check, out, train)
 
-    def _render(self, inputs, hit_lists, debug, persons, check, out_bufs=None):
+    def _render(self, inputs, hit_lists, debug, persons, check, out_bufs=None, train=None):
         lib = L.lib()
         dev = self.device
         uv = _dev(inputs["uv"].reshape(-1, 2), dev)
@@ -303,6 +306,24 @@ class Renderer:
             sc.hit_count[k] = h.numel()
             sc.hit_count_dev[k] = cnt.data_ptr() if cnt is not None else None
         sc.bg_field = self.bg.handle if self.bg is not None else None
+        keep_train = []
+        z_eik = {}
+        if train is not None:
+            assert not dev_counts, "training mode needs host-side hit counts"
+            tr = L.Train()
+            for k in range(Pn):
+                rs, kp = sampler_rng_struct(train["rng"][k], dev)
+                keep_train += [rs, kp]
+                tr.rng[k] = C.pointer(rs)
+                z_eik[k] = torch.empty(hits[k][0].numel(), device=dev)
+                tr.z_eik[k] = z_eik[k].data_ptr()
+            tb = train.get("t_rand_bg")
+            if tb is not None:
+                tb = _dev(tb, dev)
+                keep_train.append(tb)
+                tr.t_rand_bg = tb.data_ptr()
+            keep_train.append(tr)
+            sc.train = C.pointer(tr)
         need = lib.mp_render_workspace_bytes(C.byref(sc), R)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -341,11 +362,27 @@ class Renderer:
                 out.normals[k] = dbg[f"normals_{k}"].data_ptr()
         L.check(lib.mp_render_rays(C.byref(sc), uv.data_ptr(), pose.data_ptr(), K.data_ptr(), R, C.byref(out),
                                    self._ws.data_ptr(), self._ws.numel(), L.stream_ptr()), "mp_render_rays")
-        self._keep = (uv, pose, K, hits)
+        self._keep = (uv, pose, K, hits, keep_train)
+        for k, v in z_eik.items():
+            dbg[f"z_eik_{k}"] = v
         if check:
             self.check_status()
         res.update(dbg)
         return res
+
+
+def sampler_rng_struct(rng, dev):
+    """mp_sampler_rng_t from the tabled draws of ``ErrorBoundSampler.draw_training_rng`` (t_rand [R,E], u_final [R,S],
+    extra_perm [T,T*E] int32, eik_idx [T,R] int32, t_rand_bg [T,R,32]); returns (struct, tensors to keep alive)."""
+    keep = {"t_rand": rng["t_rand"].to(device=dev, dtype=torch.float32).contiguous(),
+            "u_final": rng["u_final"].to(device=dev, dtype=torch.float32).contiguous(),
+            "extra_perm": rng["extra_perm"].to(device=dev, dtype=torch.int32).contiguous(),
+            "eik_idx": rng["eik_idx"].to(device=dev, dtype=torch.int32).contiguous(),
+            "t_rand_bg": rng["t_rand_bg"].to(device=dev, dtype=torch.float32).contiguous()}
+    r = L.SamplerRng()
+    for k, v in keep.items():
+        setattr(r, k, v.data_ptr())
+    return r, keep
 
 
 class GraphedRender:

@@ -142,8 +142,7 @@ class Multiply(nn.Module):
         servers live on the device (model.smpl.SMPLServer): SMPL forward, culling, sampling, MLPs and compositing
         are all enqueued asynchronously."""
         if self.training:
-            raise NotImplementedError("training-mode forward/backward is a 'next' row (SURVEY.md §8f-1); "
-                                      "call .eval() — validation/test steps do (multiply_model.py:982,1624)")
+            return self._forward_train_values(input, id, cond_zero_shit)
         dev = input["uv"].device
         smpl_params, smpl_pose = input["smpl_params"], input["smpl_pose"]
         scale = smpl_params[:, :, 0]
@@ -230,6 +229,92 @@ class Multiply(nn.Module):
         finally:
             r.bg = bg_saved
         return {k: out[k] for k in ("acc_map", "acc_person_list", "rgb_values", "fg_rgb_values", "normal_values")}
+
+    # ---- Multiply.forward, training branch: VALUES only ------------------------------------------
+    def _forward_train_values(self, input, id=-1, cond_zero_shit=False):
+        """The values of the training branch of Multiply.forward (multiply.py:174-598 with self.training) for the shipped
+        loss weights (smpl_surface_weight = zero_pose_weight = 0, confs/model/*.yaml:77-88) at current_epoch >= 250 (the
+        earlier epochs need kaolin's point-to-mesh test, :152-166, absent offline): stochastic sampling with the
+        reference's own random stream (the same torch.manual_seed gives the same sample depths), no outlier clamp (:142 is
+        eval-only), eikonal samples and their SDF gradients (:320-331), temporal loss (:242-243), jittered background
+        depths (:482).  NO autograd graph is built: the tensors are detached values — the backward pass is the open half of
+        SURVEY.md 8f-1.  One scalar read per person keeps the random stream in step with the reference's
+        (its trip count decides how much randperm consumes)."""
+        epoch = int(input["current_epoch"])
+        if epoch < 250:
+            raise NotImplementedError("current_epoch < 250 needs kaolin's point-to-mesh test for index_off_surface "
+                                      "(multiply.py:152-166, :313-316), absent offline")
+        dev = input["uv"].device
+        smpl_params, smpl_pose = input["smpl_params"], input["smpl_pose"]
+        scale = smpl_params[:, :, 0]
+        smpl_shape, smpl_trans = input["smpl_shape"], input["smpl_trans"]
+        P = smpl_trans.shape[1]
+        person_list = list(range(P)) if id == -1 else [int(id)]
+        zero_cond = epoch < 20 or epoch % 20 == 0 or cond_zero_shit          # multiply.py:271-273
+        dirs, cam = rend_util.get_camera_params(input["uv"], input["pose"], input["intrinsics"])
+        dirs = dirs[0]
+        R = dirs.shape[0]
+        cam = cam.expand(R, 3).contiguous()
+        hits_in = input.get("index_ray_box_list")
+        persons, hits, rngs, grad_theta = {}, [], [], []
+        first = self._renderer is None
+        outs = {}
+        for i in range(P):
+            outs[i] = self.smpl_server_list[i](scale[:, i], smpl_trans[:, i], smpl_pose[:, i], smpl_shape[:, i])
+        if first:
+            self._ensure_renderer(dev, [self._person_dict(i, outs[i], smpl_pose[:, i, 3:] / np.pi) for i in range(P)])
+        r = self._ensure_renderer(dev)
+        for k, i in enumerate(person_list):
+            cond = smpl_pose[:, i, 3:] * 0. if zero_cond else smpl_pose[:, i, 3:] / np.pi
+            pd = dict(verts_p=outs[i]["smpl_verts"].reshape(-1, 3), tfs=outs[i]["smpl_tfs"].reshape(24, 4, 4), cond=cond)
+            persons[i] = pd
+            r.update_person(i, pd)
+            if hits_in is not None:
+                h = hits_in[i] if len(hits_in) == P else hits_in[k]
+            else:
+                v = pd["verts_p"]
+                lo, hi = v.min(0)[0], v.max(0)[0]
+                h = engine.ray_box_hits(cam, dirs, ((lo + hi) / 2).tolist(), ((hi - lo) / 2 * 1.2).tolist())
+            if h.numel() == 0:
+                h = torch.zeros(1, dtype=torch.int64, device=dev)                  # multiply.py:262-263
+            h = h.to(dev)
+            hits.append(h)
+            # the reference's draws for this person, in its order: get_z_vals (ray_sampler.py:38,171,202,212,216) ...
+            rng = self.ray_sampler.draw_training_rng(h.numel())
+            d, o = dirs[h].contiguous(), cam[h].contiguous()
+            self.ray_sampler.get_z_vals(d, o, self, {"smpl": cond}, pd["tfs"][None], False, pd["verts_p"][None], i,
+                                        rng=rng)               # decides the trip count -> the generator state
+            rng = {k2: v2 for k2, v2 in rng.items() if k2 != "states"}
+            rngs.append(rng)
+            # ... then the eikonal samples (multiply.py:320-326): randperm(V)[:512], PointInSpace(local_sigma 0.01)
+            srv = self.smpl_server_list[i]
+            vc = srv.verts_c.reshape(-1, 3).to(dev)
+            idx = torch.randperm(vc.shape[0])[:512].to(dev)
+            sample = vc[idx] + torch.randn(1, 512, 3)[0].to(dev) * 0.01
+            torch.rand(1, 0, 3)                                            # sampler.py:104-107 with global_ratio = 0
+            _, _, g = r.fields[i].implicit_forward(sample, want_feat=False, want_grad=True)
+            grad_theta.append(g)
+        t_rand_bg = torch.rand(R, 32)                                      # multiply.py:482 (UniformSampler, training)
+        if "image_id" in input:
+            frame = self.frame_latent_encoder(input["image_id"])
+        else:
+            frame = self.frame_latent_encoder(input["idx"])
+        if r.bg is not None:
+            r.bg.set_cond(frame.detach())
+        out = r.render(input, hits, persons=person_list, train=dict(rng=rngs, t_rand_bg=t_rand_bg))
+        temporal = torch.zeros(1, device=dev)
+        if epoch > 250:                                                    # multiply.py:242-243
+            temporal = torch.mean(torch.square(input["smpl_pose_last"] - input["smpl_pose"])).reshape(1).detach()
+        z1 = torch.zeros(1, device=dev)
+        res = {"rgb_values": out["rgb_values"], "normal_values": out["normal_values"], "acc_map": out["acc_map"],
+               "acc_person_list": out["acc_person_list"], "grad_theta": torch.cat(grad_theta, 0)[None],
+               "index_outside": input.get("index_outside"), "index_off_surface": None, "index_in_surface": None,
+               "interpenetration_loss": z1, "temporal_loss": temporal, "smpl_surface_loss": z1.clone(),
+               "zero_pose_loss": z1.clone(), "epoch": input["current_epoch"], "cam_loc": cam,
+               "t_list": [], "fg_rgb_values_each_person_list": [], "hitted_mask_idx": [], "mean_hitted_vertex_list": []}
+        if "sam_mask" in input:
+            res["sam_mask"] = input["sam_mask"].squeeze()
+        return res
 
     def query_oc(self, x, cond, person_id):
         """multiply.py:169-172: canonical SDF of person ``person_id`` at x [..., 3] under pose conditioning

@@ -24,7 +24,7 @@ class ErrorBoundSampler:
         self._ws = None
         self.last_trips = None
 
-    def get_z_vals(self, ray_dirs, cam_loc, model, cond, smpl_tfs, eval_mode, smpl_verts, person_id):
+    def get_z_vals(self, ray_dirs, cam_loc, model, cond, smpl_tfs, eval_mode, smpl_verts, person_id, rng=None):
         """model: object exposing ``density`` (LaplaceDensity), ``deformer_list`` and ``field_list`` —
         model.multiply.Multiply does."""
         training = bool(getattr(model, "training", False))
@@ -46,7 +46,7 @@ class ErrorBoundSampler:
         d = ray_dirs.detach().contiguous().float()
         o = cam_loc.detach().contiguous().float()
         if training:
-            return self._get_z_vals_training(lib, c, body, field, d, o, R, z, z_bg, trips, dev)
+            return self._get_z_vals_training(lib, c, body, field, d, o, R, z, z_bg, trips, dev, rng=rng)
         L.check(lib.mp_sample_rays(C.byref(c), body.handle, field.handle, d.data_ptr(), o.data_ptr(), R, z.data_ptr(),
                                    z_bg.data_ptr(), trips.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                    L.stream_ptr()), "mp_sample_rays")
@@ -84,10 +84,7 @@ class ErrorBoundSampler:
         stream — the same torch.manual_seed gives the same sample depths as the reference."""
         if rng is None:
             rng = self.draw_training_rng(R)
-        dv = {k: rng[k].to(dev).contiguous() for k in ("t_rand", "u_final", "extra_perm", "eik_idx", "t_rand_bg")}
-        r = L.SamplerRng()
-        for k, v in dv.items():
-            setattr(r, k, v.data_ptr())
+        r, dv = engine.sampler_rng_struct(rng, dev)
         z_eik = torch.empty(R, device=dev)
         L.check(lib.mp_sample_rays_train(C.byref(c), body.handle, field.handle, d.data_ptr(), o.data_ptr(), R, C.byref(r),
                                          z.data_ptr(), z_bg.data_ptr(), z_eik.data_ptr(), trips.data_ptr(),

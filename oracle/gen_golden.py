@@ -250,6 +250,7 @@ def main():
     rays_case(ref)
     grid_case(ref)
     train_sampler_case(ref)
+    train_forward_case(ref)
 
 
 def train_sampler_case(ref):
@@ -289,6 +290,111 @@ def train_sampler_case(ref):
     assert tags == ["rand", "rand", "randperm", "randint", "rand"], tags
     save("sampler_train", hits=idx, t_rand=draws[0][1], u_final=draws[1][1], extra_perm=draws[2][1],
          eik_idx=draws[3][1], t_rand_bg=draws[4][1], z_vals=z_vals, z_bg=z_bg, z_eik=z_eik, uv=inputs["uv"])
+
+
+def train_forward_case(ref):
+    """The TRAINING branch of Multiply.forward (multiply.py:174-598 with self.training, shipped loss weights, epoch >= 250)
+    driven line by line with the reference's own objects, as ref_forward does for the eval branch: per person
+    get_z_vals(training) -> sdf_func_with_smpl_deformer (no outlier clamp) -> eikonal samples and gradients
+    (:320-331) -> get_rbg_value(is_training=True); then the nerfacc block, the second inverse-sphere draw (:482) and
+    the background.  Every random tensor drawn on the way is recorded in draw order."""
+    Multiply = ref.multiply.Multiply
+    sc = S.make_scene(P=2, S=16, seed=42)
+    m = build_ref_model(ref, sc)
+    m.train()
+    inputs = S.make_rays(sc, 40, seed=33, region="boxes")
+    hits = S.make_hit_lists(sc, inputs)
+    ray_dirs, cam_loc = ref.rend_util.get_camera_params(inputs["uv"], inputs["pose"], inputs["intrinsics"])
+    R = ray_dirs.shape[1]
+    cam_loc = cam_loc.unsqueeze(1).repeat(1, R, 1).reshape(-1, 3)
+    ray_dirs = ray_dirs.reshape(-1, 3)
+    draws = []
+    orig = (torch.rand, torch.randperm, torch.randint, torch.randn_like)
+
+    def rec(fn, tag):
+        def w(*a, **k):
+            out = fn(*a, **k)
+            draws.append((tag, out.clone()))
+            return out
+        return w
+    torch.rand, torch.randperm, torch.randint, torch.randn_like = (rec(orig[0], "rand"), rec(orig[1], "randperm"),
+                                                                  rec(orig[2], "randint"), rec(orig[3], "randn_like"))
+    out = {}
+    try:
+        torch.manual_seed(4321)
+        torch.set_grad_enabled(True)
+        fg_rgb_list, nrm_list, sdf_list, z_list, zmax_list, idx_list, grad_theta_list, z_eik_list = [], [], [], [], [], [], [], []
+        for pid in range(2):
+            person = sc["persons"][pid]
+            idx = hits[pid].long()
+            cam_i, dir_i = cam_loc[idx], ray_dirs[idx]
+            cond = {"smpl": person["smpl_pose"][:, 3:] / np.pi}
+            smpl_tfs, smpl_verts = person["tfs"][None], person["verts_p"][None]
+            (z_vals, _), z_eik = m.ray_sampler.get_z_vals(dir_i, cam_i, m, cond, smpl_tfs, eval_mode=False,
+                                                          smpl_verts=smpl_verts, person_id=pid)
+            z_max, z_vals = z_vals[:, -1], z_vals[:, :-1]
+            N = z_vals.shape[1]
+            npx = cam_i.shape[0]
+            pts = (cam_i.unsqueeze(1) + z_vals.unsqueeze(2) * dir_i.unsqueeze(1)).reshape(-1, 3)
+            sdf_output, canonical_points, feature_vectors = m.sdf_func_with_smpl_deformer(pts, cond, smpl_tfs,
+                                                                                         smpl_verts=smpl_verts, person_id=pid)
+            # multiply.py:320-331 (smpl_server_list[pid].verts_c = the deformer's canonical vertices)
+            smpl_verts_c = person["verts_c"][None]
+            indices = torch.randperm(smpl_verts_c.shape[1])[:512]
+            verts_c = torch.index_select(smpl_verts_c, 1, indices)
+            sample = ref.sampler_cls().get_points(verts_c, global_ratio=0.)
+            sample.requires_grad_()
+            local_pred = m.foreground_implicit_network_list[pid](sample, cond, person_id=pid)[..., 0:1]
+            grad_theta_list.append(Multiply_gradient(ref, sample, local_pred).detach())
+            dirs = dir_i.unsqueeze(1).repeat(1, N, 1)
+            fg_rgb_flat, others = m.get_rbg_value(pts, canonical_points.reshape(-1, 3), -dirs.reshape(-1, 3), cond, smpl_tfs,
+                                                  feature_vectors=feature_vectors, person_id=pid, is_training=True)
+            fg_rgb_list.append(fg_rgb_flat.detach().reshape(-1, N, 3))
+            nrm_list.append(others["normals"].detach().reshape(-1, N, 3))
+            sdf_list.append(sdf_output.detach().reshape(npx, N))
+            z_list.append(z_vals)
+            zmax_list.append(z_max)
+            idx_list.append(idx)
+            z_eik_list.append(z_eik)
+        fg_rgb, normal, acc, acc_p, bg_T = port.composite_nerfacc(idx_list, z_list, zmax_list, sdf_list, fg_rgb_list, nrm_list,
+                                                                 [0, 1], R, sc["beta_param"])
+        z_vals_bg = m.ray_sampler.inverse_sphere_sampler.get_z_vals(ray_dirs, cam_loc, m)          # multiply.py:482
+        z_vals_bg = z_vals_bg * (1. / m.ray_sampler.scene_bounding_sphere)
+        z_vals_bg = torch.flip(z_vals_bg, dims=[-1, ])
+        N_bg = z_vals_bg.shape[1]
+        bg_dirs = ray_dirs.unsqueeze(1).repeat(1, N_bg, 1)
+        bg_locs = cam_loc.unsqueeze(1).repeat(1, N_bg, 1)
+        bg_points = m.depth2pts_outside(bg_locs, bg_dirs, z_vals_bg)
+        with torch.no_grad():
+            bg_output = m.bg_implicit_network(bg_points.reshape(-1, 4), {"frame": sc["frame_code"]})[0]
+            bg_ro = m.bg_rendering_network(None, None, bg_dirs.reshape(-1, 3), None, bg_output[:, 1:], sc["frame_code"])
+            bg_weights = m.bg_volume_rendering(z_vals_bg, bg_output[:, :1])
+            bg_rgb_values = torch.sum(bg_weights.unsqueeze(-1) * bg_ro.reshape(-1, N_bg, 3), 1)
+        rgb_values = fg_rgb + bg_T.unsqueeze(-1) * bg_rgb_values
+        out = dict(rgb_values=rgb_values, normal_values=normal, acc_map=acc, acc_person_list=acc_p,
+                   grad_theta=torch.cat(grad_theta_list, dim=1), uv=inputs["uv"])
+        for pid in range(2):
+            out[f"hits_{pid}"] = idx_list[pid]
+            out[f"z_vals_{pid}"] = z_list[pid]
+            out[f"sdf_{pid}"] = sdf_list[pid]
+            out[f"z_eik_{pid}"] = z_eik_list[pid]
+    finally:
+        torch.rand, torch.randperm, torch.randint, torch.randn_like = orig
+    tags = [t for t, _ in draws]
+    per = ["rand", "rand", "randperm", "randint", "rand", "randperm", "randn_like", "rand"]
+    assert tags == per + per + ["rand"], tags
+    for pid in range(2):
+        d = draws[8 * pid: 8 * pid + 8]
+        out[f"t_rand_{pid}"], out[f"u_final_{pid}"], out[f"extra_perm_{pid}"] = d[0][1], d[1][1], d[2][1]
+        out[f"eik_idx_{pid}"], out[f"t_rand_bg_sampler_{pid}"] = d[3][1], d[4][1]
+        out[f"eik_perm_{pid}"], out[f"eik_noise_{pid}"] = d[5][1], d[6][1]
+    out["t_rand_bg"] = draws[16][1]
+    save("forward_train", **out)
+
+
+def Multiply_gradient(ref, inputs, outputs):
+    """multiply.py:728-738 (module-level `gradient`)."""
+    return ref.multiply.gradient(inputs, outputs)
 
 
 def grid_case(ref):
@@ -368,5 +474,7 @@ if __name__ == "__main__":
             grid_case(_ref)
         if "sampler_train" in sys.argv[2:]:
             train_sampler_case(_ref)
+        if "forward_train" in sys.argv[2:]:
+            train_forward_case(_ref)
     else:
         main()

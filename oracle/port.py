@@ -695,8 +695,20 @@ def composite_nerfacc(index_ray_box_list, z_vals_list, z_max_list, sdf_list, rgb
 # --------------------------------------------------------------------------------------
 
 
-def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_samples=False):
-    """Multiply.forward eval branch.
+def eikonal_gradients(person, cfg, sample):
+    """multiply.py:326-331 + gradient() (:728-738): d sdf / d x at the eikonal sample points [N,3] -> [N,3]."""
+    x = sample.detach().clone().requires_grad_(True)
+    out = implicit_forward(person["implicit"], x, person["cond"], cfg["multires"])
+    return torch.autograd.grad(out[:, :1], x, torch.ones_like(out[:, :1]))[0].detach()
+
+
+def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_samples=False, train=None):
+    """Multiply.forward: eval branch, or — with ``train`` — the VALUES of the training branch for the shipped loss weights
+    at current_epoch >= 250 (multiply.py:312-331, 393-484, 548-588; no smpl-surface / zero-pose / kaolin terms).
+    ``train`` = dict(rng=[per person draws of get_z_vals, see error_bound_get_z_vals], eik_points=[per person [N,3]
+    eikonal sample points, i.e. verts_c[randperm[:512]] + randn * 0.01, multiply.py:322-326 / sampler.py:100-103],
+    t_rand_bg=[R,32] the draw of the second inverse-sphere call (:482)); adds 'grad_theta' [1, sum N, 3] and
+    '_z_eik' to the output.
 
     scene: dict(cfg, persons=[dict(implicit, render, verts_p, verts_c, weights, tfs, cond)],
                 bg_implicit, bg_render, frame_code, beta_param)
@@ -710,7 +722,7 @@ def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_
     ray_dirs = ray_dirs.reshape(-1, 3)
     P = len(scene["persons"])
     zs, zmaxs, sdfs, rgbs, nrms, idxs = [], [], [], [], [], []
-    trips = []
+    trips, z_eiks, grad_theta = [], [], []
     for p in range(P):
         person = scene["persons"][p]
         idx = hit_lists[p]
@@ -718,13 +730,19 @@ def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_
             idx = torch.tensor([0], dtype=torch.int64)          # multiply.py:262-263
         co, do = cam_loc[idx], ray_dirs[idx]
         st = {}
-        z_vals, _ = error_bound_get_z_vals(do, co, person, cfg, scene["beta_param"], stats=st)
+        if train is not None:
+            z_vals, _, z_eik = error_bound_get_z_vals(do, co, person, cfg, scene["beta_param"], stats=st,
+                                                      rng=train["rng"][p])
+            z_eiks.append(z_eik)
+            grad_theta.append(eikonal_gradients(person, cfg, train["eik_points"][p]))
+        else:
+            z_vals, _ = error_bound_get_z_vals(do, co, person, cfg, scene["beta_param"], stats=st)
         trips.append(st["trips"])
         z_max = z_vals[:, -1]
         z_vals = z_vals[:, :-1]
         n = z_vals.shape[1]
         pts = (co.unsqueeze(1) + z_vals.unsqueeze(2) * do.unsqueeze(1)).reshape(-1, 3)
-        sdf, x_c, _ = sdf_func_with_smpl_deformer(pts, person, cfg)
+        sdf, x_c, _ = sdf_func_with_smpl_deformer(pts, person, cfg, training=train is not None)
         rgb, nrm = get_rbg_value(x_c, person, cfg)
         zs.append(z_vals)
         zmaxs.append(z_max)
@@ -736,7 +754,13 @@ def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_
                                                          scene["beta_param"])
     if with_bg:
         tb = torch.linspace(0., 1., steps=32)
-        z_bg = (torch.zeros(R, 1) * (1. - tb) + torch.ones(R, 1) * tb) * (1. / cfg["scene_bounding_sphere"])
+        z_bg = torch.zeros(R, 1) * (1. - tb) + torch.ones(R, 1) * tb
+        if train is not None:      # the inverse-sphere UniformSampler sees model.training (ray_sampler.py:32-40)
+            mids = .5 * (z_bg[..., 1:] + z_bg[..., :-1])
+            upper = torch.cat([mids, z_bg[..., -1:]], -1)
+            lower = torch.cat([z_bg[..., :1], mids], -1)
+            z_bg = lower + (upper - lower) * train["t_rand_bg"]
+        z_bg = z_bg * (1. / cfg["scene_bounding_sphere"])
         bg_rgb = background_rgb(ray_dirs, cam_loc, scene, z_bg)
     else:
         bg_rgb = torch.ones_like(fg_rgb)
@@ -748,6 +772,9 @@ def multiply_forward(scene, inputs, hit_lists, with_bg=True, stats=None, return_
         "fg_rgb_values": fg_rgb + bg_T.unsqueeze(-1) * torch.ones_like(fg_rgb),
         "normal_values": normal,
     }
+    if train is not None:
+        out["grad_theta"] = torch.cat(grad_theta, 0).unsqueeze(0)       # multiply.py:564 (cat over persons, dim 1)
+        out["_z_eik"] = z_eiks
     if stats is not None:
         stats["trips"] = trips
     if return_samples:

@@ -112,6 +112,7 @@ def load():
     ns.rend_util = importlib.import_module("lib.utils.rend_util")
     ns.multiply = importlib.import_module("lib.model.multiply")
     ns.lbs = importlib.import_module("lib.smpl.lbs")
+    ns.sampler_cls = importlib.import_module("lib.model.sampler").PointInSpace       # multiply.py:67
     ns.AttrDict = AttrDict
     _loaded["ns"] = ns
     return ns

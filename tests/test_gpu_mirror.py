@@ -227,6 +227,36 @@ def test_sampler_training_mode(golden_dir):
         m.eval()
 
 
+def test_forward_training_values(golden_dir):
+    """f1, forward half: Multiply.forward with model.training (values of the training branch: stochastic sampling, no
+    outlier clamp, eikonal gradients, jittered background) against the reference's own objects driven through that
+    branch (tests/golden/forward_train.npz) — the mirror replays the reference's random stream from the same seed."""
+    import os
+    from multiply_b200 import engine
+    engine.set_engine("tc")
+    g = np.load(os.path.join(golden_dir, "forward_train.npz"))
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 40, seed=33, region="boxes")
+    assert np.array_equal(inp["uv"].numpy(), g["uv"])
+    m = _build(sc)
+    inputs = _drop_in_inputs(sc, inp, 2, [torch.from_numpy(g[f"hits_{p}"]).cuda() for p in range(2)])
+    inputs["current_epoch"] = 251
+    inputs["smpl_pose_last"] = inputs["smpl_pose"] + 0.01
+    m.train()
+    try:
+        torch.manual_seed(4321)
+        out = m(inputs)
+        torch.cuda.synchronize()
+    finally:
+        m.eval()
+    assert out["index_off_surface"] is None and out["grad_theta"].shape == (1, 1024, 3)
+    assert abs(float(out["temporal_loss"]) - 1e-4) < 1e-6
+    assert float(np.abs(out["grad_theta"].cpu().numpy() - g["grad_theta"]).max()) < 1e-4
+    for k, tol in (("rgb_values", 1e-4), ("acc_map", 1e-4), ("acc_person_list", 1e-4), ("normal_values", 1e-3)):
+        d = np.abs(out[k].cpu().numpy() - g[k])
+        assert np.median(d) < 1e-5 and d.max() < tol, (k, float(d.max()))
+
+
 def test_load_reference_checkpoint_keys():
     """A Lightning checkpoint of the reference (keys 'model.*', plus smpl_server_list / deformer_list buffers and
     MultiplyModel's body_model_list, train.py:16-22) loads through load_reference_checkpoint with strict=True."""

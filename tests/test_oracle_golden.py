@@ -149,3 +149,38 @@ def test_sampler_training_mode(golden_dir):
     dz = np.abs(z.numpy() - g["z_vals"])
     assert np.median(dz) < 1e-6 and dz.max() < 5e-3          # coarse 16/32/8 sampler: see test_forward_golden_coarse
     assert np.abs(z_eik.numpy() - g["z_eik"]).max() < 5e-3
+
+
+def _train_inputs(g, sc):
+    """The `train` argument of port.multiply_forward / Renderer.render from the recorded draws of the reference."""
+    rng, eik = [], []
+    for p in range(2):
+        rng.append({"t_rand": torch.from_numpy(g[f"t_rand_{p}"]), "u_final": torch.from_numpy(g[f"u_final_{p}"]),
+                    "extra_perm": torch.from_numpy(g[f"extra_perm_{p}"]), "eik_idx": torch.from_numpy(g[f"eik_idx_{p}"]),
+                    "t_rand_bg": torch.from_numpy(g[f"t_rand_bg_sampler_{p}"])})
+        vc = sc["persons"][p]["verts_c"]
+        idx = torch.from_numpy(g[f"eik_perm_{p}"])[:512]
+        eik.append(vc[idx] + torch.from_numpy(g[f"eik_noise_{p}"])[0] * 0.01)        # sampler.py:100-103, local_sigma 0.01
+    return dict(rng=rng, eik_points=eik, t_rand_bg=torch.from_numpy(g["t_rand_bg"]))
+
+
+def test_forward_training_mode(golden_dir):
+    """port.multiply_forward(train=...) — the VALUES of Multiply.forward's training branch (stochastic sampling, no
+    outlier clamp, eikonal gradients, jittered background depths) — against the reference's own objects driven through
+    that branch with the same random draws."""
+    g = _g(golden_dir, "forward_train")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inputs = S.make_rays(sc, 40, seed=33, region="boxes")
+    assert np.array_equal(inputs["uv"].numpy(), g["uv"])
+    hits = [torch.from_numpy(g[f"hits_{p}"]) for p in range(2)]
+    st = {}
+    out = port.multiply_forward(sc, inputs, hits, stats=st, return_samples=True, train=_train_inputs(g, sc))
+    assert [t * sc["cfg"]["N_samples_eval"] for t in st["trips"]] == [g[f"extra_perm_{p}"].shape[0] for p in range(2)]
+    assert np.abs(out["grad_theta"].numpy() - g["grad_theta"]).max() < 2e-6
+    for p in range(2):
+        dz = np.abs(out["_z_vals"][p].numpy() - g[f"z_vals_{p}"])
+        assert np.median(dz) < 1e-6 and dz.max() < 5e-3
+    # coarse 16/32/8 sampler: pixels inherit the depth jitter of the inverse-CDF step (see test_forward_golden_coarse)
+    for k, tol in (("rgb_values", 1e-5), ("acc_map", 1e-5), ("normal_values", 5e-4), ("acc_person_list", 1e-5)):
+        d = np.abs(out[k].numpy() - g[k])
+        assert np.median(d) < 1e-5 and d.max() < tol, (k, float(d.max()))
