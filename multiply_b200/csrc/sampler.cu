@@ -65,12 +65,14 @@ __global__ void tables_kernel(SamplerTables t, int E, int S, int X, int max_iter
 }
 
 // uniform initial samples + Lemma-2 beta bound     ray_sampler.py:21-42, :70-76
+// One warp per ray: lane l owns samples l, l+32, ... (coalesced stores of the ray's row; the one-thread-per-ray version
+// wrote 256 values at a 5 KB stride each: 38 us for 2300 rays).
 __global__ void sampler_init_kernel(const float* __restrict__ dirs, const float* __restrict__ cam, int R, float r,
                                     float near, int E, const float* __restrict__ tvals, float bound_coef,
                                     float* __restrict__ z, int zcap, float* __restrict__ beta,
                                     float* __restrict__ far_out, SamplerState* st, const int* __restrict__ R_dev,
                                     const float* __restrict__ t_rand) {
-  int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (R_dev) R = min(R, *R_dev);     // device-side row count (hit list culled on the GPU, no host sync)
   if (ray >= R) return;
   const float* o = cam + 3 * ray;
@@ -79,28 +81,32 @@ __global__ void sampler_init_kernel(const float* __restrict__ dirs, const float*
   float dot = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
   float nrm = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
   float under = dot * dot - (nrm * nrm - r * r);
-  if (!(under > 0.f)) atomicOr(&st->bad_sphere, 1);
+  if (lane == 0 && !(under > 0.f)) atomicOr(&st->bad_sphere, 1);
   float far = fmaxf(sqrtf(under) * 1.f - dot, 0.f);
-  far_out[ray] = far;
+  if (lane == 0) far_out[ray] = far;
   float* zr = z + (size_t)ray * zcap;
-  float prev = 0.f, sum = 0.f;
   auto zu = [&](int j) { float t = tvals[j]; return near * (1.f - t) + far * t; };
-  for (int j = 0; j < E; ++j) {
+  // sample j (training mode, model.training: stratified in the interval between the midpoints, ray_sampler.py:32-40)
+  auto zs = [&](int j) {
     float zj = zu(j);
     if (t_rand) {
-      // training mode (model.training): stratified samples in the intervals between the midpoints   ray_sampler.py:32-40
       float lower = (j == 0) ? zj : .5f * (zj + zu(j - 1));
       float upper = (j == E - 1) ? zj : .5f * (zu(j + 1) + zj);
       zj = lower + (upper - lower) * t_rand[(size_t)ray * E + j];
     }
+    return zj;
+  };
+  float sum = 0.f;
+  for (int j = lane; j < E; j += 32) {
+    float zj = zs(j);
     zr[j] = zj;
     if (j > 0) {
-      float dd = zj - prev;
+      float dd = zj - zs(j - 1);
       sum += dd * dd;
     }
-    prev = zj;
   }
-  beta[ray] = sqrtf(bound_coef * sum);
+  sum = warp_sum(sum);
+  if (lane == 0) beta[ray] = sqrtf(bound_coef * sum);
 }
 
 // ---- per-ray warp routines -------------------------------------------------------------------
@@ -183,7 +189,10 @@ __global__ void sampler_beta_kernel(const float* __restrict__ z, const float* __
   float err = error_bound_warp(sz, ss, sd, M, beta0, lane);
   if (err <= eps) beta = beta0;
   float bmin = beta0, bmax = beta;
-  for (int j = 0; j < beta_iters; ++j) {
+  // a ray whose error at beta0 is already within eps has bmin == bmax == beta0: every bisection step would evaluate
+  // mid = beta0 again and leave the bracket unchanged (ray_sampler.py:116-121), so the loop is skipped — bit-identical
+  const int iters = (bmin == bmax) ? 0 : beta_iters;
+  for (int j = 0; j < iters; ++j) {
     float mid = (bmin + bmax) / 2.f;
     err = error_bound_warp(sz, ss, sd, M, mid, lane);
     if (err <= eps) bmax = mid;
@@ -470,7 +479,7 @@ int sample_rays(const mp_sampler_cfg_t& c, const Body& body, const Field& field,
   tables_kernel<<<div_up(tn, 128), 128, 0, st>>>(w.tab, E, S, X, c.max_total_iters,
                                                  (float)(1.0 / c.scene_bounding_sphere), w.st);
   MP_LAUNCH_CHECK();
-  sampler_init_kernel<<<div_up(R, 128), 128, 0, st>>>(dirs, cam, R, c.scene_bounding_sphere, c.near, E, w.tab.u_E,
+  sampler_init_kernel<<<div_up(R * 32, 128), 128, 0, st>>>(dirs, cam, R, c.scene_bounding_sphere, c.near, E, w.tab.u_E,
                                                       bound_coef, w.zA, zcap, w.beta, w.far, w.st, R_dev, rng.t_rand);
   MP_LAUNCH_CHECK();
   float *zc = w.zA, *zn = w.zB, *sc = w.sA, *sn = w.sB;
