@@ -25,6 +25,8 @@ struct Smpl {
   float* tfs_c_inv;          // [24,16]
   float* verts_c;            // [V,3]
   float* tmp_tfs;            // [24,16]
+  float* J_t;                // [24,3]     J_regressor @ v_template           (precomputed at creation)
+  float* J_s;                // [24,3,10]  J_regressor @ shapedirs: J(betas) = J_t + J_s . betas
 };
 
 __device__ __forceinline__ void mat4_mul(const float* a, const float* b, float* c) {
@@ -39,6 +41,37 @@ __device__ __forceinline__ void mat4_mul(const float* a, const float* b, float* 
     }
 }
 
+// Joint regression is linear in the shape coefficients: J = Jr @ (v_template + shapedirs . betas) (lbs.py:184-188) =
+// Jr @ v_template + (Jr @ shapedirs) . betas.  The two regressed tensors are computed once per model (one warp per joint),
+// which takes the 24 x V regression -- 58 of the SMPL server's 90 us per call -- out of the per-frame path.
+__global__ void __launch_bounds__(1024) smpl_jreg_kernel(Smpl m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= MP_NUM_JOINTS) return;
+  const float* jr = m.J_regressor + (size_t)warp * m.V;
+  float acc[33];
+#pragma unroll
+  for (int k = 0; k < 33; ++k) acc[k] = 0.f;
+  for (int v = lane; v < m.V; v += 32) {
+    const float w = jr[v];
+    if (w == 0.f) continue;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      acc[a] = fmaf(w, m.v_template[3 * v + a], acc[a]);
+      const float* sd = m.shapedirs + ((size_t)3 * v + a) * 10;
+#pragma unroll
+      for (int l = 0; l < 10; ++l) acc[3 + a * 10 + l] = fmaf(w, sd[l], acc[3 + a * 10 + l]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 33; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) {
+      m.J_t[warp * 3 + a] = acc[a];
+      for (int l = 0; l < 10; ++l) m.J_s[(warp * 3 + a) * 10 + l] = acc[3 + a * 10 + l];
+    }
+  }
+}
+
 // one CTA of 1024 threads
 __global__ void __launch_bounds__(1024) smpl_pose_kernel(Smpl m, const float* __restrict__ scale_p,
                                                          const float* __restrict__ transl, const float* __restrict__ thetas,
@@ -51,34 +84,12 @@ __global__ void __launch_bounds__(1024) smpl_pose_kernel(Smpl m, const float* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 10) sb[tid] = betas[tid];
   __syncthreads();
-  // v_shaped = v_template + blend_shapes(betas, shapedirs)      lbs.py:184, :252-273
-  for (int i = tid; i < m.V * 3; i += blockDim.x) {
-    const float* sd = m.shapedirs + (size_t)i * 10;
-    float s = 0.f;
+  // J = J_regressor @ v_shaped (lbs.py:188, :232-249) through the precomputed regressions (smpl_jreg_kernel)
+  if (tid < MP_NUM_JOINTS * 3) {
+    float j = m.J_t[tid];
 #pragma unroll
-    for (int l = 0; l < 10; ++l) s = fmaf(sb[l], sd[l], s);
-    m.v_shaped[i] = m.v_template[i] + s;
-  }
-  __threadfence_block();
-  __syncthreads();
-  // J = J_regressor @ v_shaped      lbs.py:188, :232-249  (one warp per joint)
-  if (warp < MP_NUM_JOINTS) {
-    const float* jr = m.J_regressor + (size_t)warp * m.V;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int v = lane; v < m.V; v += 32) {
-      float w = jr[v];
-      a0 = fmaf(w, m.v_shaped[3 * v], a0);
-      a1 = fmaf(w, m.v_shaped[3 * v + 1], a1);
-      a2 = fmaf(w, m.v_shaped[3 * v + 2], a2);
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    if (lane == 0) {
-      sJ[warp][0] = a0;
-      sJ[warp][1] = a1;
-      sJ[warp][2] = a2;
-    }
+    for (int l = 0; l < 10; ++l) j = fmaf(sb[l], m.J_s[tid * 10 + l], j);
+    sJ[tid / 3][tid % 3] = j;
   }
   // Rodrigues      lbs.py:276-307
   if (tid < MP_NUM_JOINTS) {
@@ -151,9 +162,11 @@ __global__ void __launch_bounds__(1024) smpl_pose_kernel(Smpl m, const float* __
 // per vertex: pose blend shapes + skinning + SMPLServer's scale/translation
 //   v_posed = v_shaped + pose_feature @ posedirs ; T = W @ A ; verts = T v_posed      lbs.py:201-227, smpl.py:78
 // A_abs already carries the scale and translation: (s*A_rot) v + (s*A_t + t*s) = s*(A v) + t*s.
-__global__ void smpl_skin_kernel(Smpl m, float* __restrict__ verts_out) {
+__global__ void smpl_skin_kernel(Smpl m, const float* __restrict__ betas, float* __restrict__ verts_out) {
   __shared__ float spf[207];
   __shared__ float sA[MP_NUM_JOINTS * 16];
+  __shared__ float sb[10];
+  if (threadIdx.x < 10) sb[threadIdx.x] = betas[threadIdx.x];
   for (int i = threadIdx.x; i < 207; i += blockDim.x) spf[i] = m.pose_feature[i];
   for (int i = threadIdx.x; i < MP_NUM_JOINTS * 16; i += blockDim.x) sA[i] = m.A_abs[i];
   __syncthreads();
@@ -168,7 +181,17 @@ __global__ void smpl_skin_kernel(Smpl m, float* __restrict__ verts_out) {
     p1 = fmaf(f, pd[1], p1);
     p2 = fmaf(f, pd[2], p2);
   }
-  float x = m.v_shaped[3 * v] + p0, y = m.v_shaped[3 * v + 1] + p1, z = m.v_shaped[3 * v + 2] + p2;
+  // v_shaped = v_template + blend_shapes(betas, shapedirs)      lbs.py:184, :252-273
+  float vs[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float* sd = m.shapedirs + ((size_t)3 * v + a) * 10;
+    float sacc = 0.f;
+#pragma unroll
+    for (int l = 0; l < 10; ++l) sacc = fmaf(sb[l], sd[l], sacc);
+    vs[a] = m.v_template[3 * v + a] + sacc;
+  }
+  float x = vs[0] + p0, y = vs[1] + p1, z = vs[2] + p2;
   float T[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) T[k] = 0.f;
@@ -208,7 +231,7 @@ static int smpl_run(const Smpl& m, const float* scale, const float* transl, cons
                     int absolute, float* verts, float* tfs, cudaStream_t st) {
   smpl_pose_kernel<<<1, 1024, 0, st>>>(m, scale, transl, thetas, betas, absolute, tfs);
   MP_LAUNCH_CHECK();
-  smpl_skin_kernel<<<div_up(m.V, 128), 128, 0, st>>>(m, verts);
+  smpl_skin_kernel<<<div_up(m.V, 128), 128, 0, st>>>(m, betas, verts);
   MP_LAUNCH_CHECK();
   return 0;
 }
@@ -223,7 +246,7 @@ extern "C" {
 
 size_t mp_smpl_bytes(int V) {
   return mp::align_up((size_t)V * 3 * 4, 256) * 2 + 256 * 8 + mp::align_up(207 * 4, 256) + 3 * mp::align_up(24 * 16 * 4, 256) +
-         mp::align_up(86 * 4, 256) + 4096;
+         mp::align_up(86 * 4, 256) + mp::align_up(24 * 3 * 4, 256) + mp::align_up(24 * 3 * 10 * 4, 256) + 4096;
 }
 
 int mp_smpl_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* J_regressor,
@@ -250,6 +273,8 @@ int mp_smpl_create(const float* v_template, const float* shapedirs, const float*
   m.A_abs = a.take<float>(24 * 16);
   m.tfs_c_inv = a.take<float>(24 * 16);
   m.tmp_tfs = a.take<float>(24 * 16);
+  m.J_t = a.take<float>(24 * 3);
+  m.J_s = a.take<float>(24 * 3 * 10);
   float* canon = a.take<float>(86);
   if (!a.ok) {
     delete h;
@@ -271,6 +296,8 @@ int mp_smpl_create(const float* v_template, const float* shapedirs, const float*
     return -2;
   }
   const float* betas = betas_canonical ? betas_canonical : canon + 76;
+  smpl_jreg_kernel<<<1, 1024, 0, st>>>(m);
+  g_launches++;
   int rc = smpl_run(m, canon, canon + 1, canon + 4, betas, 1, m.verts_c, m.tmp_tfs, st);
   if (rc == 0) {
     affine_inverse_kernel<<<1, 32, 0, st>>>(m.tmp_tfs, m.tfs_c_inv, 24);
