@@ -164,6 +164,20 @@ int mp_deform_inverse(mp_body_t* b, const float* x, int N, float* x_c, uint8_t* 
  * the upper-left 3x3 of sum_j w_j tfs_j with w from the nearest CANONICAL vertex. */
 int mp_deform_forward_jac(mp_body_t* b, const float* x_c, int N, float* x_d, float* Jinv, void* stream);
 
+/* Optional root finder (BASELINE.json north_star: "Broyden-root-finds canonical points").  The
+ * reference has NO such step (its deformer is KNN + closed-form inverse LBS, deformer.py:19-50), so
+ * this is non-default and checked against its own CPU restatement (oracle/port.py:deform_broyden), not against MultiPly.
+ * Solves forward_skinning(x_c) = x (deformer.py:31-35: weights of the nearest CANONICAL vertex) by Broyden's method
+ * started from the closed-form inverse (weights of the nearest POSED vertex), J^-1 initialised with the inverse
+ * blended 3x3 at the start point, at most max_steps rank-one updates, lowest-residual iterate returned.
+ *   x [N,3] -> x_c [N,3]; residual [N] = |forward_skinning(x_c) - x| (NULL ok); converged [N] = residual <
+ *   cvg_threshold (NULL ok); outlier [N] as mp_deform_inverse (NULL ok); steps [N] iterations taken (NULL ok). */
+int mp_deform_broyden(mp_body_t* b, const float* x, int N, int max_steps, float cvg_threshold, float* x_c,
+                      float* residual, uint8_t* converged, uint8_t* outlier, int* steps, void* stream);
+/* max_steps > 0 makes every inverse-deformer call on this body (mp_deform_inverse, mp_sdf_with_deformer, the sampler
+ * and the main pass of mp_render_rays) refine its non-outlier points this way; 0 (the default) = reference behaviour. */
+int mp_body_set_root_finder(mp_body_t* b, int max_steps, float cvg_threshold);
+
 /* ------------------------------------------------------------------------------------------
  * density: LaplaceDensity (lib/model/density.py:11-29)
  * ---------------------------------------------------------------------------------------- */

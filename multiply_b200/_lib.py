@@ -110,6 +110,8 @@ SIGNATURES = {
     "mp_body_set_pose": (_I, [_VP, _VP, _VP, _VP]),
     "mp_deform_inverse": (_I, [_VP, _VP, _I, _VP, _VP, _I, _VP]),
     "mp_deform_forward_jac": (_I, [_VP, _VP, _I, _VP, _VP, _VP]),
+    "mp_deform_broyden": (_I, [_VP, _VP, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mp_body_set_root_finder": (_I, [_VP, _I, _F]),
     "mp_laplace_density": (_I, [_VP, _I, _F, _VP, _VP]),
     "mp_camera_rays": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP]),
     "mp_sphere_intersections": (_I, [_VP, _VP, _I, _F, _VP, _VP, _VP]),

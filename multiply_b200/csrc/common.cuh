@@ -106,6 +106,9 @@ struct Body {
   float4* posed_sorted;
   int* scratch;              // [kMaxCells + 8]
   float4* vert_tf;           // [V][3] per-vertex inverse blended transform: rows (I_r0, I_r1, I_r2, c_r), x_c = I (x - c)
+  // optional root finder (mp_body_set_root_finder): 0 steps = the reference's closed-form inverse only
+  int root_steps;
+  float root_thr;
 };
 
 // packed network (mlp_pack.cu)

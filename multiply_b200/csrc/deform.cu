@@ -275,7 +275,84 @@ __global__ void vertex_tf_kernel(const float* __restrict__ weights, const float*
   vert_tf[3 * (size_t)v + 2] = make_float4(I[6], I[7], I[8], T[11] * is);
 }
 
-// Shared per-point routine of the inverse deformer.
+// ---- optional root finder --------------------------------------------------------------
+// The closed-form inverse picks the skinning weights of the nearest POSED vertex, the forward map
+// (deformer.py:31-35, forward_skinning) those of the nearest CANONICAL vertex of x_c; where the two disagree
+// forward_skinning(x_c) != x_d.  Broyden's method on g(x_c) = forward_skinning(x_c) - x_d, started from the
+// closed-form inverse with J^-1 = the inverse blended 3x3 at the start point (the weights are detached, so that IS the
+// Jacobian inside a Voronoi cell), rank-one "good Broyden" updates of J^-1 (Sherman-Morrison), lowest-residual
+// iterate kept.  The reference has no such step; parity is against oracle/port.py:deform_broyden.
+__device__ __forceinline__ void skin_forward_point(const Body& b, const GridHeader& gc, const float x[3], float f[3],
+                                                   int& vi) {
+  float d2;
+  nearest_vertex(gc, b.cano_cell_start, b.cano_sorted, b.V, x[0], x[1], x[2], true, d2, vi);
+  float T[12], s;
+  blend_tf(b.weights + (size_t)vi * MP_NUM_JOINTS, b.tfs, T, s);
+  f[0] = fmaf(T[0], x[0], fmaf(T[1], x[1], fmaf(T[2], x[2], T[3])));
+  f[1] = fmaf(T[4], x[0], fmaf(T[5], x[1], fmaf(T[6], x[2], T[7])));
+  f[2] = fmaf(T[8], x[0], fmaf(T[9], x[1], fmaf(T[10], x[2], T[11])));
+}
+
+__device__ __noinline__ void broyden_refine(const Body& b, float px, float py, float pz, int max_steps, float thr,
+                                            float xc[3], float& resid, int& steps) {
+  const GridHeader gc = *b.cano_hdr;
+  float x[3] = {xc[0], xc[1], xc[2]}, f[3], g[3];
+  int vi;
+  skin_forward_point(b, gc, x, f, vi);
+  g[0] = f[0] - px;
+  g[1] = f[1] - py;
+  g[2] = f[2] - pz;
+  float Ji[9];
+  {
+    const float4 r0 = __ldg(&b.vert_tf[3 * (size_t)vi]), r1 = __ldg(&b.vert_tf[3 * (size_t)vi + 1]),
+                 r2 = __ldg(&b.vert_tf[3 * (size_t)vi + 2]);
+    Ji[0] = r0.x; Ji[1] = r0.y; Ji[2] = r0.z; Ji[3] = r1.x; Ji[4] = r1.y; Ji[5] = r1.z; Ji[6] = r2.x; Ji[7] = r2.y;
+    Ji[8] = r2.z;
+  }
+  float best = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  steps = 0;
+  for (int k = 0; k < max_steps && best >= thr; ++k) {
+    float dx[3], gn[3], dg[3], u[3], vt[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dx[r] = -(Ji[3 * r] * g[0] + Ji[3 * r + 1] * g[1] + Ji[3 * r + 2] * g[2]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) x[r] += dx[r];
+    skin_forward_point(b, gc, x, f, vi);
+    gn[0] = f[0] - px;
+    gn[1] = f[1] - py;
+    gn[2] = f[2] - pz;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dg[r] = gn[r] - g[r];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) u[r] = Ji[3 * r] * dg[0] + Ji[3 * r + 1] * dg[1] + Ji[3 * r + 2] * dg[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vt[c] = dx[0] * Ji[c] + dx[1] * Ji[3 + c] + dx[2] * Ji[6 + c];
+    float den = dx[0] * u[0] + dx[1] * u[1] + dx[2] * u[2];
+    if (fabsf(den) > 1e-20f) {
+      float id = 1.0f / den;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ji[3 * r + c] += (dx[r] - u[r]) * vt[c] * id;
+    }
+    g[0] = gn[0];
+    g[1] = gn[1];
+    g[2] = gn[2];
+    float rn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    steps = k + 1;
+    if (rn < best) {
+      best = rn;
+      xc[0] = x[0];
+      xc[1] = x[1];
+      xc[2] = x[2];
+    }
+  }
+  resid = best;
+}
+
+// Shared per-point routine of the inverse deformer.  ROOT = false is the reference's path; the ROOT = true
+// instantiations exist so that the optional refinement costs the default kernels neither registers nor stack.
+template <bool ROOT = false>
 __device__ __forceinline__ void deform_inverse_point(const Body& b, const GridHeader& g, float px, float py, float pz,
                                                      bool exact_far, float xc[3], bool& outlier) {
   float d2;
@@ -298,8 +375,37 @@ __device__ __forceinline__ void deform_inverse_point(const Body& b, const GridHe
   xc[0] = r0.x * qx + r0.y * qy + r0.z * qz;
   xc[1] = r1.x * qx + r1.y * qy + r1.z * qz;
   xc[2] = r2.x * qx + r2.y * qy + r2.z * qz;
+  if (ROOT && b.root_steps > 0 && !outlier) {   // non-default (row f4); outliers keep the closed form (their SDF is forced to 4)
+    float resid;
+    int steps;
+    broyden_refine(b, px, py, pz, b.root_steps, b.root_thr, xc, resid, steps);
+  }
 }
 
+__global__ void deform_broyden_kernel(Body b, const float* __restrict__ x, int N, int max_steps, float thr,
+                                      float* __restrict__ x_c, float* __restrict__ residual,
+                                      uint8_t* __restrict__ converged, uint8_t* __restrict__ outlier,
+                                      int* __restrict__ steps_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  GridHeader g = *b.posed_hdr;
+  float xc[3];
+  bool o;
+  float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+  deform_inverse_point<false>(b, g, px, py, pz, true, xc, o);
+  float resid;
+  int steps;
+  broyden_refine(b, px, py, pz, max_steps, thr, xc, resid, steps);
+  x_c[3 * i] = xc[0];
+  x_c[3 * i + 1] = xc[1];
+  x_c[3 * i + 2] = xc[2];
+  if (residual) residual[i] = resid;
+  if (converged) converged[i] = resid < thr ? 1 : 0;
+  if (outlier) outlier[i] = o ? 1 : 0;
+  if (steps_out) steps_out[i] = steps;
+}
+
+template <bool ROOT>
 __global__ void deform_inverse_kernel(Body b, const float* __restrict__ x, int N, float* __restrict__ x_c,
                                       uint8_t* __restrict__ outlier, int exact_far) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,7 +413,7 @@ __global__ void deform_inverse_kernel(Body b, const float* __restrict__ x, int N
   GridHeader g = *b.posed_hdr;
   float xc[3];
   bool o;
-  deform_inverse_point(b, g, x[3 * i], x[3 * i + 1], x[3 * i + 2], exact_far != 0, xc, o);
+  deform_inverse_point<ROOT>(b, g, x[3 * i], x[3 * i + 1], x[3 * i + 2], exact_far != 0, xc, o);
   x_c[3 * i] = xc[0];
   x_c[3 * i + 1] = xc[1];
   x_c[3 * i + 2] = xc[2];
@@ -318,6 +424,7 @@ __global__ void deform_inverse_kernel(Body b, const float* __restrict__ x, int N
 //   points = cam_loc + z * ray_dirs        (ray_sampler.py:82, multiply.py:295)
 // `slot[i]` gives where the SDF of point i has to land; outliers get sdf = 4 right here
 // (multiply.py:142-143) and everything else is appended to the compact work list of the MLP.
+template <bool ROOT>
 __global__ void deform_rays_kernel(Body b, const float* __restrict__ dirs, const float* __restrict__ cam,
                                    const float* __restrict__ z, int z_stride, const int* __restrict__ zpos,
                                    int zpos_stride, int n_per_ray, int R, int prune, float* __restrict__ sdf_out,
@@ -341,7 +448,7 @@ __global__ void deform_rays_kernel(Body b, const float* __restrict__ dirs, const
     float pz = __fadd_rn(cam[3 * r + 2], __fmul_rn(zz, dirs[3 * r + 2]));
     GridHeader g = *b.posed_hdr;
     bool o;
-    deform_inverse_point(b, g, px, py, pz, prune == 0, xc, o);
+    deform_inverse_point<ROOT>(b, g, px, py, pz, prune == 0, xc, o);
     slot = r * sdf_stride + col;
     if (outlier_out) outlier_out[slot] = o ? 1 : 0;
     if (o && prune) {
@@ -412,9 +519,14 @@ int launch_deform_rays(const Body& b, const float* dirs, const float* cam, const
                        const int* active, cudaStream_t st, const int* R_dev) {
   int total = R * n_per_ray;
   if (total <= 0) return 0;
-  deform_rays_kernel<<<div_up(total, 128), 128, 0, st>>>(b, dirs, cam, z, z_stride, zpos, zpos_stride, n_per_ray, R,
-                                                         prune, sdf_out, sdf_stride, xc_list, slot_list, count,
-                                                         outlier_out, active, R_dev);
+  if (b.root_steps > 0)
+    deform_rays_kernel<true><<<div_up(total, 128), 128, 0, st>>>(b, dirs, cam, z, z_stride, zpos, zpos_stride,
+                                                               n_per_ray, R, prune, sdf_out, sdf_stride, xc_list,
+                                                               slot_list, count, outlier_out, active, R_dev);
+  else
+    deform_rays_kernel<false><<<div_up(total, 128), 128, 0, st>>>(b, dirs, cam, z, z_stride, zpos, zpos_stride,
+                                                                n_per_ray, R, prune, sdf_out, sdf_stride, xc_list,
+                                                                slot_list, count, outlier_out, active, R_dev);
   MP_LAUNCH_CHECK();
   return 0;
 }
@@ -455,6 +567,8 @@ int mp_body_create(const float* verts_cano, const float* weights, int V, float c
   b.verts_cano = verts_cano;
   b.verts_posed = nullptr;
   b.tfs = nullptr;
+  b.root_steps = 0;
+  b.root_thr = 1e-5f;
   b.cano_cell = cano_cell;
   b.cano_hdr = a.take<mp::GridHeader>(1);
   b.posed_hdr = a.take<mp::GridHeader>(1);
@@ -498,8 +612,34 @@ int mp_deform_inverse(mp_body_t* h, const float* x, int N, float* x_c, uint8_t* 
                       void* stream) {
   MP_REQUIRE(h && h->b.tfs, "mp_deform_inverse: body has no pose (call mp_body_set_pose)");
   if (N <= 0) return 0;   // deformer.py:20
-  mp::deform_inverse_kernel<<<mp::div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(h->b, x, N, x_c, outlier,
-                                                                                   exact_far);
+  if (h->b.root_steps > 0)
+    mp::deform_inverse_kernel<true><<<mp::div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(h->b, x, N, x_c, outlier,
+                                                                                           exact_far);
+  else
+    mp::deform_inverse_kernel<false><<<mp::div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(h->b, x, N, x_c, outlier,
+                                                                                            exact_far);
+  MP_LAUNCH_CHECK();
+  return 0;
+}
+
+int mp_body_set_root_finder(mp_body_t* h, int max_steps, float cvg_threshold) {
+  MP_REQUIRE(h, "mp_body_set_root_finder: null body");
+  MP_REQUIRE(max_steps >= 0 && max_steps <= 64, "mp_body_set_root_finder: max_steps %d outside [0, 64]", max_steps);
+  MP_REQUIRE(cvg_threshold > 0.f, "mp_body_set_root_finder: threshold must be positive");
+  h->b.root_steps = max_steps;
+  h->b.root_thr = cvg_threshold;
+  return 0;
+}
+
+int mp_deform_broyden(mp_body_t* h, const float* x, int N, int max_steps, float cvg_threshold, float* x_c,
+                      float* residual, uint8_t* converged, uint8_t* outlier, int* steps, void* stream) {
+  MP_REQUIRE(h && h->b.tfs, "mp_deform_broyden: body has no pose (call mp_body_set_pose)");
+  MP_REQUIRE(x_c, "mp_deform_broyden: null output");
+  MP_REQUIRE(max_steps >= 0 && max_steps <= 64 && cvg_threshold > 0.f, "mp_deform_broyden: bad iteration limits");
+  if (N <= 0) return 0;
+  MP_REQUIRE(x, "mp_deform_broyden: null input");
+  mp::deform_broyden_kernel<<<mp::div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(
+      h->b, x, N, max_steps, cvg_threshold, x_c, residual, converged, outlier, steps);
   MP_LAUNCH_CHECK();
   return 0;
 }

@@ -178,6 +178,27 @@ class Body:
                                           int(exact_far), L.stream_ptr()), "mp_deform_inverse")
         return xc, out.bool()
 
+    def deform_broyden(self, x, max_steps=10, cvg_threshold=1e-5):
+        """Root of forward_skinning(x_c) = x by Broyden's method from the closed-form inverse (row f4, not in the
+        reference): returns dict(x_c, residual, converged, outlier, steps)."""
+        x = _dev(x, self.device)
+        N = x.shape[0]
+        xc = torch.empty(N, 3, device=self.device)
+        res = torch.empty(N, device=self.device)
+        conv = torch.empty(N, dtype=torch.uint8, device=self.device)
+        out = torch.empty(N, dtype=torch.uint8, device=self.device)
+        steps = torch.empty(N, dtype=torch.int32, device=self.device)
+        L.check(L.lib().mp_deform_broyden(self.handle, x.data_ptr(), N, int(max_steps), float(cvg_threshold),
+                                          xc.data_ptr(), res.data_ptr(), conv.data_ptr(), out.data_ptr(),
+                                          steps.data_ptr(), L.stream_ptr()), "mp_deform_broyden")
+        return dict(x_c=xc, residual=res, converged=conv.bool(), outlier=out.bool(), steps=steps)
+
+    def set_root_finder(self, max_steps, cvg_threshold=1e-5):
+        """max_steps > 0: every inverse-deformer call on this body refines its non-outlier points with Broyden
+        iterations (mp_body_set_root_finder); 0 restores the reference's closed-form inverse."""
+        L.check(L.lib().mp_body_set_root_finder(self.handle, int(max_steps), float(cvg_threshold)),
+                "mp_body_set_root_finder")
+
     def forward_jac(self, xc):
         xc = _dev(xc, self.device)
         N = xc.shape[0]

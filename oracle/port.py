@@ -217,8 +217,63 @@ def skinning(x, w, tfs, inverse=False):
 def deform_inverse(x, person):
     """SMPLDeformer.forward(inverse=True, return_weights=False), deformer.py:19-30."""
     w, outlier = query_skinning_weights(x[None], person["verts_p"], person["weights"][None])
-    xc = skinning(x.unsqueeze(0), w, person["tfs"][None], inverse=True)
-    return xc.squeeze(0), outlier
+    xc = skinning(x.unsqueeze(0), w, person["tfs"][None], inverse=True).squeeze(0)
+    rf = person.get("root_finder")          # row f4 (non-default, not in the reference): see deform_broyden
+    if rf and x.shape[0] > 0:
+        keep = ~outlier
+        if bool(keep.any()):
+            xr, _, _, _ = deform_broyden(x[keep], dict(person, root_finder=None), rf[0], rf[1])
+            xc = xc.clone()
+            xc[keep] = xr
+    return xc, outlier
+
+
+def forward_skinning(x_c, person):
+    """SMPLDeformer.forward_skinning, deformer.py:31-35: weights of the nearest CANONICAL vertex, forward LBS.
+    Returns (x_d [N,3], A [N,3,3] = upper-left block of the blended transform)."""
+    w, _ = query_skinning_weights(x_c[None], person["verts_c"], person["weights"][None])
+    T = torch.einsum("bpn,bnij->bpij", w, person["tfs"][None])[0]
+    x_d = torch.einsum("pij,pj->pi", T[:, :3, :3], x_c) + T[:, :3, 3]
+    return x_d, T[:, :3, :3]
+
+
+def deform_broyden(x, person, max_steps=10, cvg_threshold=1e-5):
+    """Row f4 — NOT a restatement of reference code: the reference has no root finder.  This is
+    the CPU statement of the algorithm mp_deform_broyden implements, anchored on the two reference maps it connects:
+    start = the closed-form inverse (deformer.py:19-30), residual g(x_c) = forward_skinning(x_c) - x
+    (deformer.py:31-35).  Broyden's method with J^-1 initialised to the inverse blended 3x3 at the start point,
+    Sherman-Morrison rank-one updates, lowest-residual iterate kept.  Returns (x_c, residual, converged, outlier)."""
+    xc, outlier = deform_inverse(x, person)
+    xc = xc.clone()
+    f, A = forward_skinning(xc, person)
+    Ji = torch.linalg.inv(A)
+    g = f - x
+    best = g.norm(dim=-1)
+    cur = xc.clone()
+    for _ in range(max_steps):
+        act = best >= cvg_threshold
+        if not bool(act.any()):
+            break
+        idx = act.nonzero()[:, 0]
+        dx = -torch.einsum("pij,pj->pi", Ji[idx], g[idx])
+        xn = cur[idx] + dx
+        fn, _ = forward_skinning(xn, person)
+        gn = fn - x[idx]
+        dg = gn - g[idx]
+        u = torch.einsum("pij,pj->pi", Ji[idx], dg)
+        vt = torch.einsum("pi,pij->pj", dx, Ji[idx])
+        den = (dx * u).sum(-1)
+        ok = den.abs() > 1e-20
+        upd = (dx - u)[:, :, None] * vt[:, None, :] / torch.where(ok, den, torch.ones_like(den))[:, None, None]
+        Ji[idx] = Ji[idx] + torch.where(ok[:, None, None], upd, torch.zeros_like(upd))
+        cur[idx] = xn
+        g[idx] = gn
+        rn = gn.norm(dim=-1)
+        better = rn < best[idx]
+        bi = idx[better]
+        best[bi] = rn[better]
+        xc[bi] = xn[better]
+    return xc, best, best < cvg_threshold, outlier
 
 
 def sdf_func_with_smpl_deformer(x, person, cfg, chunk=65536, training=False):

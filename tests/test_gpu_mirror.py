@@ -396,7 +396,9 @@ def test_sequence_directory_drives_forward(tmp_path):
     assert torch.allclose(frame["pose"].cpu(), pose, atol=1e-5)
     assert torch.allclose(frame["intrinsics"][0, :3, :3].cpu(), K[0, :3, :3], rtol=1e-5, atol=1e-3)
     assert torch.equal(frame["uv"].cpu(), base["uv"].cpu())
-    assert torch.allclose(frame["smpl_params"].cpu(), base["smpl_params"].cpu(), atol=1e-7)
+    assert torch.allclose(frame["smpl_params"][..., 0].cpu(), base["smpl_params"][..., 0].cpu(), atol=1e-7)
+    for k in ("smpl_pose", "smpl_trans", "smpl_shape"):
+        assert torch.allclose(frame[k].cpu(), base[k].cpu(), atol=1e-7), k
 
     whole = model(frame)
     chunks = idr_utils.render_full_frame(model, frame, seq.total_pixels, n_pixels=seq.total_pixels)

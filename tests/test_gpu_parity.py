@@ -165,6 +165,70 @@ def test_deformer(golden_dir, scene64):
     assert _maxabs(xc2.cpu().numpy()[m], g["x_c"][m]) < 1e-5
 
 
+def test_deform_broyden(scene64):
+    """Row f4 (non-default; the reference has no root finder): mp_deform_broyden against oracle/port.py:deform_broyden."""
+    from multiply_b200 import engine
+    from oracle import port
+    p1 = scene64["persons"][1]
+    g = torch.Generator().manual_seed(0)
+    v = p1["verts_p"]
+    x = v[torch.randint(0, v.shape[0], (6000,), generator=g)] + 0.04 * torch.randn(6000, 3, generator=g)
+    b = engine.Body(p1["verts_c"], p1["weights"], cano_cell=0.2)
+    b.set_pose(p1["verts_p"], p1["tfs"])
+    xc0, outl0 = b.deform_inverse(x)
+    o = b.deform_broyden(x, 10, 1e-5)
+    ref_xc, ref_res, ref_conv, ref_out = port.deform_broyden(x, p1, 10, 1e-5)
+    assert torch.equal(o["outlier"].cpu(), ref_out) and torch.equal(outl0.cpu(), ref_out)
+    # the reported residual is the residual of the returned point (forward skinning on the device)
+    xd, _ = b.forward_jac(o["x_c"])
+    assert float(((xd - x.cuda()).norm(dim=-1) - o["residual"]).abs().max()) < 2e-6
+    # consistent points (closed-form residual below the threshold) take no step and are bit-equal to mp_deform_inverse
+    still = o["steps"] == 0
+    assert 0.3 < float(still.float().mean()) < 0.95
+    assert torch.equal(o["x_c"][still], xc0[still])
+    assert bool((o["residual"][still] < 1e-5).all())
+    # against the CPU statement: same verdicts, same roots
+    conv = o["converged"].cpu()
+    assert float((conv == ref_conv).float().mean()) > 0.995
+    both = conv & ref_conv
+    assert float(both.float().mean()) > 0.85
+    assert float((o["x_c"].cpu()[both] - ref_xc[both]).abs().max()) < 1e-4
+    assert float((o["x_c"].cpu() - ref_xc).abs().max(dim=-1)[0].gt(1e-4).float().mean()) < 0.01
+    # the switch: every inverse-deformer call refines non-outliers, outliers keep the closed form
+    b.set_root_finder(10, 1e-5)
+    xc1, outl1 = b.deform_inverse(x)
+    m = ~outl1
+    assert torch.equal(outl1, outl0)
+    assert torch.equal(xc1[m], o["x_c"][m]) and torch.equal(xc1[~m], xc0[~m])
+    b.set_root_finder(0)
+    assert torch.equal(b.deform_inverse(x)[0], xc0)
+
+
+@pytest.mark.parametrize("eng", ENGINES)
+def test_forward_with_root_finder(eng):
+    """The whole path with the root finder switched on for every body (sampler, main pass, normals at the refined
+    canonical points) against the oracle with the same switch."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine(eng)
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 128, seed=9, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    sc_ref = dict(sc, persons=[dict(p, root_finder=(10, 1e-5)) for p in sc["persons"]])
+    ref = port.multiply_forward(sc_ref, inp, hits)
+    plain = port.multiply_forward(sc, inp, hits)
+    r = engine.Renderer(sc)
+    for b in r.bodies:
+        b.set_root_finder(10, 1e-5)
+    o = r.render(inp, hits)
+    torch.cuda.synchronize()
+    assert _maxabs(ref["rgb_values"].numpy(), plain["rgb_values"].numpy()) > 1e-3      # the switch matters here
+    for k in ("rgb_values", "acc_map", "normal_values"):
+        d = np.abs(o[k].cpu().numpy() - ref[k].numpy()).reshape(128, -1).max(1)
+        assert (d > 1e-4).mean() < 0.03, (k, float(d.max()), float((d > 1e-4).mean()))
+        assert np.median(d) < 1e-5, k
+
+
 def test_density(golden_dir):
     from multiply_b200 import _lib as L
     g = _g(golden_dir, "density")
