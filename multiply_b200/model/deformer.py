@@ -20,11 +20,21 @@ class SMPLDeformer(torch.nn.Module):
         self.smpl_weights = smpl_weights.reshape(1, -1, 24)
         self._scale = float(scale)
         self._body = None
+        self._root_finder = (0, 1e-5)
+
+    def set_root_finder(self, max_steps, cvg_threshold=1e-5):
+        """Not in the reference: max_steps > 0 refines the closed-form inverse with Broyden
+        iterations on forward_skinning(x_c) = x (engine.Body.set_root_finder); 0 = reference behaviour (default)."""
+        self._root_finder = (int(max_steps), float(cvg_threshold))
+        if self._body is not None:
+            self._body.set_root_finder(*self._root_finder)
 
     def body(self, device):
         if self._body is None or self._body.device != torch.device(device):
             self._body = engine.Body(self.smpl_verts[0], self.smpl_weights[0], cano_cell=0.1001 / max(self._scale, 1e-3),
                                      device=device)
+            if self._root_finder[0] > 0:
+                self._body.set_root_finder(*self._root_finder)
         return self._body
 
     def forward(self, x, smpl_tfs, return_weights=True, inverse=False, smpl_verts=None):

@@ -77,7 +77,22 @@ class Multiply(nn.Module):
                 persons = [self._person_dict(p, None) for p in range(len(self.smpl_server_list))]
             self._renderer = engine.Renderer(self._scene_dict(persons), device=device)
             self._key = key
+            rf = getattr(self, "_root_finder", (0, 1e-5))
+            if rf[0] > 0:
+                for b in self._renderer.bodies:
+                    b.set_root_finder(*rf)
         return self._renderer
+
+    def set_root_finder(self, max_steps, cvg_threshold=1e-5):
+        """Not in the reference (the reference's deformer is the closed-form inverse only):
+        max_steps > 0 makes the sampler, the main pass and sdf_func_with_smpl_deformer refine every non-outlier
+        canonical point with Broyden iterations on forward_skinning(x_c) = x.  0 (default) = reference behaviour."""
+        self._root_finder = (int(max_steps), float(cvg_threshold))
+        for d in self.deformer_list:
+            d.set_root_finder(*self._root_finder)
+        if self._renderer is not None:
+            for b in self._renderer.bodies:
+                b.set_root_finder(*self._root_finder)
 
     def _person_dict(self, p, smpl_out, cond=None):
         srv = self.smpl_server_list[p]

@@ -410,3 +410,28 @@ def test_sequence_directory_drives_forward(tmp_path):
         assert torch.equal(chunks[k].reshape(whole[k].shape), whole[k]), k
         bad = ((whole[k] - ref[k]).abs().reshape(res * res, -1).max(1)[0] > 1e-3).float().mean()
         assert float(bad) < 0.01, (k, float(bad))                  # camera recovered to ~1e-6: same picture
+
+
+def test_multiply_root_finder_switch():
+    """Row f4 through the mirror: Multiply.set_root_finder(10) == oracle with the same switch; (0) restores the
+    reference's closed-form path bit for bit."""
+    from multiply_b200 import engine
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 96, seed=11, region="boxes")
+    hits = S.make_hit_lists(sc, inp)
+    m = _build(sc)
+    inputs = _drop_in_inputs(sc, inp, 2, with_hits=[h.cuda() for h in hits])
+    plain = {k: v.clone() for k, v in m(inputs).items()}
+    m.set_root_finder(10, 1e-5)
+    on = {k: v.clone() for k, v in m(inputs).items()}
+    m.set_root_finder(0)
+    off = m(inputs)
+    torch.cuda.synchronize()
+    ref = port.multiply_forward(dict(sc, persons=[dict(p, root_finder=(10, 1e-5)) for p in sc["persons"]]), inp, hits)
+    assert float((on["rgb_values"] - plain["rgb_values"]).abs().max()) > 1e-3
+    for k in ("rgb_values", "normal_values", "acc_map"):
+        assert torch.equal(off[k], plain[k]), k
+        d = (on[k].cpu() - ref[k]).abs().reshape(96, -1).max(1)[0]
+        assert float((d > 1e-4).float().mean()) < 0.03 and float(d.median()) < 1e-5, (k, float(d.max()))
