@@ -52,8 +52,8 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_p
 with open(f"{out_dir}/{tag}_tc_kernel.md", "w") as f:
     f.write(f"# ncu --set full capture of `tc_chain_kernel` ({tag})\n\n")
     f.write("Command: `ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 13 -c 13 python bench.py "
-            "--steps 1 --warmup 1 --no-cpu-baseline --no-extras`.  Launch order per step: background; person 0: sdf-only x5 "
-            "(sampler trips; inactive ones exit), shade; person 1: same.\n\n")
+            "--steps 1 --warmup 1 --no-cpu-baseline --no-extras`.  Launch order per step: person 0: sdf-only x5 "
+            "(sampler trips; inactive ones exit), shade; person 1: same; the background chain last (ids 0-5 person 0, 6-11 person 1, 12 background).\n\n")
     for r in rr[2:]:
         t = r[ix["gpu__time_duration.sum"]]
         f.write(f"## launch id {r[ix['ID']]}  ({t} {units[ix['gpu__time_duration.sum']]})\n\n| metric | value | unit |\n|---|---:|---|\n")
