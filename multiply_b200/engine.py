@@ -455,10 +455,11 @@ def ray_aabb_hits(cam_loc, ray_dirs, verts, inflate=1.2):
     return idx, cnt
 
 
-def ray_box_hits(cam_loc, ray_dirs, center, half_extent, rot=None):
+def ray_box_hits(cam_loc, ray_dirs, center, half_extent, rot=None, device_count=False):
     """Device-side ray / box culling (mp_ray_box_hits): sorted int64 ray ids that hit the box.  One scalar
     device->host read for the count — the reference pays a full `.cpu()` round trip plus trimesh here
-    (multiply.py:256)."""
+    (multiply.py:256).  ``device_count=True`` returns (ids [R], count [1]) with the count left on the device and the
+    list finalised (empty -> ray 0, mp_hit_list_finalize), the form ``Renderer.render`` takes without a host read."""
     lib = L.lib()
     dev = cam_loc.device
     cam = cam_loc.detach().contiguous().float()
@@ -473,4 +474,7 @@ def ray_box_hits(cam_loc, ray_dirs, center, half_extent, rot=None):
         rot_d = torch.as_tensor(rot, dtype=torch.float64).reshape(9).to(dev).contiguous()
     L.check(lib.mp_ray_box_hits(cam.data_ptr(), d.data_ptr(), R, c, h, L.ptr(rot_d), idx.data_ptr(), cnt.data_ptr(),
                                 L.stream_ptr()), "mp_ray_box_hits")
+    if device_count:
+        L.check(lib.mp_hit_list_finalize(idx.data_ptr(), cnt.data_ptr(), L.stream_ptr()), "mp_hit_list_finalize")
+        return idx, cnt
     return idx[: int(cnt.item())]

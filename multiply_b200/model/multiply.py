@@ -6,7 +6,9 @@ Differences forced by the offline environment (documented in DESIGN.md):
     (``smpl_server_list``: objects with ``forward(scale, transl, thetas, betas) -> dict(smpl_verts, smpl_tfs,
     smpl_weights)`` and canonical ``verts_c``); ``scene.SyntheticSMPLServer`` is the offline stand-in;
   * ray/box hit lists (trimesh on the host in the reference, multiply.py:208-214,256) are taken from
-    ``input['index_ray_box_list']`` when present, else computed by a host slab test against the x1.2 box.
+    ``input['index_ray_box_list']`` when present, else computed on the device: against the x1.2 axis-aligned box of the
+    posed vertices without any host round trip (``culling="aabb"``, default), or against the x1.2 ORIENTED box built on
+    the host by ``utils/obb.py`` as the reference does with trimesh (``culling="obb"``).
 """
 import numpy as np
 import torch
@@ -21,8 +23,12 @@ from . import rend_util
 
 
 class Multiply(nn.Module):
-    def __init__(self, opt, betas_path=None, smpl_server_list=None, num_person=None):
+    def __init__(self, opt, betas_path=None, smpl_server_list=None, num_person=None, culling="aabb"):
         super().__init__()
+        if culling not in ("aabb", "obb"):
+            raise ValueError("culling must be 'aabb' (device-side axis-aligned box, no host round trip) or 'obb' "
+                             "(oriented box on the host as in multiply.py:208-214)")
+        self.culling = culling
         if smpl_server_list is None:
             raise ValueError("SMPL model files are not redistributable: pass smpl_server_list")
         self.using_nerfacc = True
@@ -218,7 +224,15 @@ class Multiply(nn.Module):
                 if need_rays:
                     # multiply.py:208-214, :256-263: rays vs the person's box inflated by 1.2 — box, test, ordered
                     # compaction and the empty-list rule all on the device; the count stays there
-                    hits.append(engine.ray_aabb_hits(cam, dirs, pd["verts_p"], 1.2))
+                    if self.culling == "obb":
+                        # the reference's choice: oriented box of the posed mesh, extents x1.2, built on the host from
+                        # a device->host copy of the vertices (multiply.py:208-214); utils/obb.py restates trimesh's
+                        # algorithm.  The ray test itself stays on the device.
+                        from ..utils import obb
+                        c, h, rot = obb.culling_box(pd["verts_p"].detach().cpu().numpy(), 1.2)
+                        hits.append(engine.ray_box_hits(cam, dirs, c, h, rot, device_count=True))
+                    else:
+                        hits.append(engine.ray_aabb_hits(cam, dirs, pd["verts_p"], 1.2))
                 if st is not main:
                     ev = torch.cuda.Event()
                     ev.record(st)

@@ -435,3 +435,49 @@ def test_multiply_root_finder_switch():
         assert torch.equal(off[k], plain[k]), k
         d = (on[k].cpu() - ref[k]).abs().reshape(96, -1).max(1)[0]
         assert float((d > 1e-4).float().mean()) < 0.03 and float(d.median()) < 1e-5, (k, float(d.max()))
+
+
+def test_oriented_box_culling():
+    """culling='obb' (multiply.py:208-214: oriented box of the posed mesh, extents x1.2, built on the host): the device
+    ray test against that box equals a float64 slab test in the box frame, and the forward runs on those lists and
+    equals the oracle fed with the same lists."""
+    from multiply_b200 import engine
+    from multiply_b200.model import rend_util
+    from multiply_b200.utils import obb
+    from oracle import port
+    engine.set_engine("tc")
+    sc = S.make_scene(P=2, S=16, seed=42)
+    inp = S.make_rays(sc, 160, seed=21, region="image")
+    P = 2
+    servers = [S.SyntheticSMPLServer(p, P) for p in range(P)]
+    from multiply_b200.model.multiply import Multiply
+    m = Multiply(OPT, smpl_server_list=servers, culling="obb")
+    m.load_state_dict(_build(sc).state_dict())
+    m = m.cuda().eval()
+    inputs = _drop_in_inputs(sc, inp, P)
+    out = m(inputs)
+    torch.cuda.synchronize()
+    # the same lists on the host
+    dirs, cam = rend_util.get_camera_params_host(inp["uv"], inp["pose"], inp["intrinsics"])
+    cam = cam.reshape(-1, 3)[:1]
+    d64, c64 = dirs.double().numpy(), cam.double().numpy()
+    hits, persons = [], []
+    for p in range(P):
+        o = servers[p](inputs["smpl_params"][:, p, 0].cpu(), inputs["smpl_trans"][:, p].cpu(), inputs["smpl_pose"][:, p].cpu(),
+                       inputs["smpl_shape"][:, p].cpu())
+        v = o["smpl_verts"][0]
+        persons.append(dict(sc["persons"][p], verts_p=v, tfs=o["smpl_tfs"][0]))
+        c, h, rot = obb.culling_box(v.numpy(), 1.2)
+        o_l = (c64 - c) @ rot.T
+        d_l = d64 @ rot.T
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t1, t2 = (-h - o_l) / d_l, (h - o_l) / d_l
+        tn, tf = np.minimum(t1, t2).max(1), np.maximum(t1, t2).min(1)
+        ids = np.nonzero((tn <= tf) & (tf >= 0))[0]
+        dev_ids = engine.ray_box_hits(cam.expand(160, 3).contiguous().cuda(), dirs.cuda(), c, h, rot)
+        assert np.array_equal(dev_ids.cpu().numpy(), ids)
+        assert 0 < len(ids) < 160                                 # a real cull: some rays hit, some miss
+        hits.append(torch.from_numpy(ids if len(ids) else np.array([0])).long())
+    ref = port.multiply_forward(dict(sc, persons=persons), inp, hits)
+    for k in ("rgb_values", "acc_map", "acc_person_list"):
+        assert float((out[k].cpu() - ref[k]).abs().max()) < 1e-4, k
