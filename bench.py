@@ -596,6 +596,11 @@ def main():
             tiles = pp[k] / 128.0
             issued += tiles * steps_nk[k] * 3 * 2.0 * 128 * 256 * 64
         line["roofline"]["issued_tensor_tflops"] = issued / (mlp_ms / 1000.0) / 1e12 if mlp_ms > 0 else 0.0
+        line["roofline"]["issued_frac_of_peak"] = line["roofline"]["issued_tensor_tflops"] / peaks["bf16_sustained"]
+        line["roofline"]["note"] = ("parity mode issues three fp16 MMAs per product (A_hi.W_hi + A_lo.W_hi + A_hi.W_lo) and "
+                                    "pads K / N to 64 / 256: `frac` counts the ALGORITHMIC FLOPs once, so its ceiling in "
+                                    "this mode is ~1/3; `issued_frac_of_peak` is the tensor work actually issued against "
+                                    "the same measured peak")
         if not args.no_cpu_baseline:
             from oracle import port
             n_sample = CPU_SAMPLE_RAYS
