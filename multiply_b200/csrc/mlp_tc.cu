@@ -204,12 +204,19 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = make_uint4(*(uint32_t*)&l[0], *(uint32_t*)&l[1], *(uint32_t*)&l[2], *(uint32_t*)&l[3]);
 }
 
-__device__ __forceinline__ void store_a8(char* A, int row, int col, const float* v) {
+// 16-byte store into the operand image through a 32-bit shared-window address.  (A pointer derived from the aligned
+// dynamic-shared base loses its address space: the compiler emitted generic ST.E.128 with 64-bit address arithmetic.)
+// (volatile, no memory clobber: ordered against the volatile proxy fence / mbarrier arrive that publish the image; no
+// C++ access reads these bytes back.)
+__device__ __forceinline__ void sts128(uint32_t A32, uint32_t off, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A32 + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ void store_a8(uint32_t A32, int row, int col, const float* v) {
   uint4 hi, lo;
   split8(v, hi, lo);
   uint32_t o = a_off(row, col >> 6, (col >> 3) & 7);
-  *reinterpret_cast<uint4*>(A + o) = hi;
-  *reinterpret_cast<uint4*>(A + 65536 + o) = lo;
+  sts128(A32, o, hi);
+  sts128(A32, 65536 + o, lo);
 }
 
 // element k of the positional embedding of x (embedders.py:8-34)
@@ -385,6 +392,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
   char* base = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   char* A = base;                                   // [hi | lo] x 4 K-blocks
+  const uint32_t A32 = smem_u32(A);
   char* ring = base + kABytes;                      // kRing weight slots
   uint64_t* bars = (uint64_t*)(ring + kRing * kSlotBytes);
   uint64_t* full = bars;                            // [kRing]
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = (c + j < E) ? emb[(size_t)(c + j) * 128 + row] : 0.f;
-          store_a8(A, row, c, v);
+          store_a8(A32, row, c, v);
         }
         arrive_all();
       }
@@ -617,7 +625,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
               xv[0] = x[0]; xv[1] = x[1]; xv[2] = x[2];
               xv[3] = nrm[0]; xv[4] = nrm[1]; xv[5] = nrm[2];
             }
-            store_a8(A, row, e0, xv);
+            store_a8(A32, row, e0, xv);
           }
           fence_async_smem();
           mbar_arrive(x_ready);
@@ -643,8 +651,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             for (int u = 0; u < 4; ++u) {
               const int chunk = (cbeg >> 3) + c8 + u;
               const uint32_t o = a_off(row, chunk >> 3, chunk & 7);
-              *reinterpret_cast<uint4*>(A + o) = fh[u];
-              *reinterpret_cast<uint4*>(A + 65536 + o) = fl[u];
+              sts128(A32, o, fh[u]);
+              sts128(A32, 65536 + o, fl[u]);
               if ((lane & 7) == 0 && !(io.knobs & 4)) {
                 discard_line(&fsc[(size_t)chunk * 128 + row], fh[u].x);
                 discard_line(&fsc[(size_t)(32 + chunk) * 128 + row], fl[u].x);
@@ -716,7 +724,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
                   st_stream(&fsc[(size_t)chunk * 128 + row], fh[j >> 3]);
                   st_stream(&fsc[(size_t)(32 + chunk) * 128 + row], fl[j >> 3]);
                 }
-                store_a8(A, row, c + j, seed + j);
+                store_a8(A32, row, c + j, seed + j);
               }
               return;
             }
@@ -833,8 +841,8 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < CW; j += 8) {
               const uint32_t o = a_off(row, (c + j) >> 6, ((c + j) >> 3) & 7);
-              *reinterpret_cast<uint4*>(A + o) = hi[j >> 3];
-              *reinterpret_cast<uint4*>(A + 65536 + o) = lo[j >> 3];
+              sts128(A32, o, hi[j >> 3]);
+              sts128(A32, 65536 + o, lo[j >> 3]);
               if (st.flags & F_STASH_FEAT) {
                 // stash the feature chunks (they come back as the colour net's input)
                 int chunk = (c + j) >> 3;
