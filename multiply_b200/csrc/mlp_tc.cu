@@ -364,6 +364,9 @@ struct KTag {
 };
 
 // cycle stamps of CTA 0 (MP_TC_KNOBS bit 1): [0..] epilogue warp 2, [2048..] MMA issuer; see mp_tc_trace_read
+#ifndef MP_TC_TRACE
+#define MP_TC_TRACE 0
+#endif
 __device__ unsigned long long g_trace[4096];
 
 // NW epilogue warps (8 or 16): warp w owns TMEM lane quadrant w % 4 (rows) and column part (w-2)/4.
@@ -473,7 +476,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             } else if (PIPE) {
               mbar_wait(&a_ready[kc], ar_ph);
               tc_fence_after();
+#if MP_TC_TRACE
               if ((io.knobs & 2) && blockIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x)) g_trace[2048 + (P.nsteps > 12 ? 0 : 1024) + s * 8 + kc] = clock64();
+#endif
             }
             // hi slot: A_hi.W_hi + A_lo.W_hi
             int r = it % kRing;
@@ -504,7 +509,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             if (kc == 0 && nk == 5) umma_commit(x_free);   // K-block 0 may be overwritten once these have completed
           }
           umma_commit(d_full);
+#if MP_TC_TRACE
           if ((io.knobs & 2) && blockIdx.x == 0 && tile == (int)(blockIdx.x + gridDim.x)) g_trace[2048 + (P.nsteps > 12 ? 0 : 1024) + s * 8 + 4] = clock64();
+#endif
           if (PIPE) {
             // keep the phases of the unused K-block barriers in step
             for (int kc = nk < 4 ? nk : 4; kc < 4; ++kc) mbar_wait(&a_ready[kc], ar_ph);
@@ -533,6 +540,13 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
     constexpr int NCH = PCOLS / CW;          // chunks per thread and step
     // first column of this thread's i-th chunk: contiguous, or 16 columns of every K-block in K order (PIPE)
     auto col_of = [&](int i) { return PIPE ? i * 64 + part * CW : cbeg + i * CW; };
+#ifndef MP_AOFF
+#define MP_AOFF 1
+#endif
+#if MP_AOFF
+    static_assert(PIPE && CW == 16, "precomputed operand offsets assume 16-column chunks in K order");
+    const uint32_t aoff0 = a_off(row, 0, (part * 2) & 7), aoff1 = a_off(row, 0, (part * 2 + 1) & 7);
+#endif
     auto arrive_all = [&]() {
       fence_async_smem();
       tc_fence_before();
@@ -630,7 +644,13 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
           fence_async_smem();
           mbar_arrive(x_ready);
         }
+        // cycle stamps of one tile (scripts/gpu_trace.py): compiled in only with -DMP_TC_TRACE=1 (scripts/build_variant.sh);
+        // even predicated off they cost ~1.5 % of the epilogue's issue slots
+#if MP_TC_TRACE
         const bool tr = (io.knobs & 2) && blockIdx.x == 0 && warp == 2 && lane == 0 && tile == (int)(blockIdx.x + gridDim.x);
+#else
+        constexpr bool tr = false;
+#endif
         unsigned long long* trp = g_trace + (P.nsteps > 12 ? 0 : 1024) + s * 8;
         if (tr) trp[0] = clock64();
         mbar_wait(d_full, df_ph);
@@ -833,22 +853,25 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1) tc_chain_kernel(const __grid_
             }
           }
           // activations of this chunk -> A (fp16 hi/lo, swizzled) unless this is the last layer
-          if (!(st.flags & (F_RGB_OUT | F_FINAL_GRAD))) {
+          // (F_FINAL_GRAD steps never get here; F_RGB_OUT exists only on ReLU steps; F_STASH_FEAT only on the seed step,
+          // which returned above -- testing them here cost seven predicated-off instructions per chunk)
+          bool to_a = true;
+          if constexpr (KIND == K_RELU) to_a = !(st.flags & F_RGB_OUT);
+          if (to_a) {
             uint4 hi[CW / 8], lo[CW / 8];
 #pragma unroll
             for (int j = 0; j < CW; j += 8) split8(v + j, hi[j >> 3], lo[j >> 3]);
             issue_next(ci);
 #pragma unroll
             for (int j = 0; j < CW; j += 8) {
+#if MP_AOFF
+              // (PIPE) chunk ci is K-block ci; the 16-byte slot inside the row depends only on the column part
+              const uint32_t o = (uint32_t)ci * 16384u + (j ? aoff1 : aoff0);
+#else
               const uint32_t o = a_off(row, (c + j) >> 6, ((c + j) >> 3) & 7);
+#endif
               sts128(A32, o, hi[j >> 3]);
               sts128(A32, 65536 + o, lo[j >> 3]);
-              if (st.flags & F_STASH_FEAT) {
-                // stash the feature chunks (they come back as the colour net's input)
-                int chunk = (c + j) >> 3;
-                st_stream(&fsc[(size_t)chunk * 128 + row], hi[j >> 3]);
-                st_stream(&fsc[(size_t)(32 + chunk) * 128 + row], lo[j >> 3]);
-              }
             }
           } else {
             issue_next(ci);
