@@ -1,4 +1,6 @@
-"""Print the cycle stamps of one tile of CTA 0 of the tcgen05 chain (MP_TC_KNOBS=2), shade program of bench config 2."""
+"""Print the cycle stamps of one tile of CTA 0 of the tcgen05 chain (MP_TC_KNOBS=2), shade program of bench config 2.
+The stamps are compiled in only with -DMP_TC_TRACE=1: `scripts/build_variant.sh trace -DMP_TC_TRACE=1`, then run this with
+MP_LIB=multiply_b200/_variants/lib_trace.so."""
 import os, ctypes as C
 os.environ["MP_TC_KNOBS"] = os.environ.get("MP_TC_KNOBS", "2")
 import torch
@@ -16,6 +18,8 @@ torch.cuda.synchronize()
 buf = (C.c_ulonglong * 4096)()
 L.check(L.lib().mp_tc_trace_read(buf, 4096), "trace")
 t = list(buf)
+if not any(t):
+    raise SystemExit("no stamps: this library was built without -DMP_TC_TRACE=1 (see the docstring)")
 # the last launch is the shade chain of the single person (the background field is skipped for P=1? print both halves anyway)
 fg = t[512:518]
 print("final-grad step: reload_done chunks_done bar1 pairs_done bar2 normal_done:", [x - min(v for v in fg if v) if x else -1 for x in fg])
