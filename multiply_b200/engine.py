@@ -465,16 +465,17 @@ def ray_box_hits(cam_loc, ray_dirs, center, half_extent, rot=None, device_count=
     cam = cam_loc.detach().contiguous().float()
     d = ray_dirs.detach().contiguous().float()
     R = cam.shape[0]
-    idx = torch.empty(R, dtype=torch.int64, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
     c = (C.c_double * 3)(*[float(v) for v in center])
     h = (C.c_double * 3)(*[float(v) for v in half_extent])
-    rot_d = None
-    if rot is not None:
-        rot_d = torch.as_tensor(rot, dtype=torch.float64).reshape(9).to(dev).contiguous()
-    L.check(lib.mp_ray_box_hits(cam.data_ptr(), d.data_ptr(), R, c, h, L.ptr(rot_d), idx.data_ptr(), cnt.data_ptr(),
-                                L.stream_ptr()), "mp_ray_box_hits")
-    if device_count:
-        L.check(lib.mp_hit_list_finalize(idx.data_ptr(), cnt.data_ptr(), L.stream_ptr()), "mp_hit_list_finalize")
-        return idx, cnt
+    with torch.cuda.device(dev):
+        idx = torch.empty(R, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        rot_d = None
+        if rot is not None:
+            rot_d = torch.as_tensor(rot, dtype=torch.float64).reshape(9).to(dev).contiguous()
+        L.check(lib.mp_ray_box_hits(cam.data_ptr(), d.data_ptr(), R, c, h, L.ptr(rot_d), idx.data_ptr(), cnt.data_ptr(),
+                                    L.stream_ptr()), "mp_ray_box_hits")
+        if device_count:
+            L.check(lib.mp_hit_list_finalize(idx.data_ptr(), cnt.data_ptr(), L.stream_ptr()), "mp_hit_list_finalize")
+            return idx, cnt
     return idx[: int(cnt.item())]
