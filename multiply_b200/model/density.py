@@ -6,10 +6,13 @@ from .. import _lib as L
 
 
 class Density(nn.Module):
-    def __init__(self, params_init={}):
+    """density.py:4-12: every entry of ``params_init`` becomes a scalar parameter of that name (``beta``); calling the
+    module evaluates ``density_func``."""
+
+    def __init__(self, params_init=None):
         super().__init__()
-        for p in params_init:
-            setattr(self, p, nn.Parameter(torch.tensor(float(params_init[p]))))
+        for name, value in dict(params_init or {}).items():
+            self.register_parameter(name, nn.Parameter(torch.as_tensor(float(value), dtype=torch.float32)))
 
     def forward(self, sdf, beta=None):
         return self.density_func(sdf, beta=beta)
@@ -18,7 +21,7 @@ class Density(nn.Module):
 class LaplaceDensity(Density):
     """density.py:15-29: alpha * Laplace(0, beta).cdf(-sdf)."""
 
-    def __init__(self, params_init={}, beta_min=0.0001):
+    def __init__(self, params_init=None, beta_min=0.0001):
         super().__init__(params_init=params_init)
         self.beta_min = float(beta_min)
 
