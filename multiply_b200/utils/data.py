@@ -66,6 +66,44 @@ def png_size(path):
     return int(h), int(w)
 
 
+def body_params_from_state_dict(state_dict):
+    """The per-person optimised SMPL parameters a Lightning checkpoint of the reference carries next to the scene model
+    (multiply_model.py:38-44,81-92: ``body_model_list.{p}`` are ``BodyModelParams`` modules, lib/model/
+    body_model_params.py:5-50, whose tables are ``nn.Embedding`` weights): returns a list over persons of
+    ``dict(betas [1,10], global_orient [F,3], body_pose [F,69], transl [F,3])``.  Empty list if the checkpoint has none
+    (a model trained with ``opt_smpl = False`` reads the poses from the data directory instead)."""
+    persons = {}
+    for key, value in state_dict.items():
+        parts = key.split(".")
+        if len(parts) == 4 and parts[0] == "body_model_list" and parts[3] == "weight":
+            persons.setdefault(int(parts[1]), {})[parts[2]] = value.detach().float()
+    out = []
+    for p in sorted(persons):
+        missing = {"betas", "global_orient", "body_pose", "transl"} - set(persons[p])
+        if missing:
+            raise KeyError("body_model_list.%d lacks %s" % (p, sorted(missing)))
+        out.append(persons[p])
+    if out and sorted(persons) != list(range(len(out))):
+        raise KeyError("body_model_list indices are not contiguous: %s" % sorted(persons))
+    return out
+
+
+def apply_body_params(inputs, body_params, frame_idx):
+    """multiply_model.py:163-170 (the ``opt_smpl`` branch): the optimised tables replace ``smpl_pose`` / ``smpl_shape`` /
+    ``smpl_trans`` of the input dict for frame ``frame_idx`` (``betas`` has a single row shared by all frames,
+    body_model_params.py:46-47).  Returns a new dict; tensors follow the device of ``inputs['smpl_params']``."""
+    dev = inputs["smpl_params"].device
+    i = int(frame_idx)
+    row = lambda t: t[i:i + 1].to(dev)
+    out = dict(inputs)
+    out["smpl_trans"] = torch.stack([row(bp["transl"]) for bp in body_params], dim=1)
+    out["smpl_shape"] = torch.stack([bp["betas"][:1].to(dev) for bp in body_params], dim=1)
+    go = torch.stack([row(bp["global_orient"]) for bp in body_params], dim=1)
+    bpose = torch.stack([row(bp["body_pose"]) for bp in body_params], dim=1)
+    out["smpl_pose"] = torch.cat((go, bpose), dim=2)
+    return out
+
+
 class SequenceData:
     """Frames ``range(start_frame, end_frame)`` of a preprocessed sequence (Hi4D.py:93-146)."""
 
@@ -137,5 +175,9 @@ class SequenceData:
             inputs = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inputs.items()}
         return inputs
 
-    def frame(self, idx, device=None):
-        return self.__getitem__(idx, device)
+    def frame(self, idx, device=None, body_params=None):
+        """Input dict of frame ``idx``; with ``body_params`` (``body_params_from_state_dict`` of a checkpoint trained with
+        ``opt_smpl``) the optimised poses / shapes / translations replace the directory's, as in
+        multiply_model.py:163-170."""
+        inputs = self.__getitem__(idx, device)
+        return apply_body_params(inputs, body_params, idx) if body_params else inputs

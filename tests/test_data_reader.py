@@ -113,3 +113,33 @@ def test_png_size_rejects_other_files(tmp_path):
     p.write_bytes(b"not a png at all, just some bytes....")
     with pytest.raises(ValueError):
         D.png_size(str(p))
+
+
+def test_body_params_from_checkpoint(tmp_path):
+    """The optimised SMPL tables of a Lightning checkpoint (body_model_list.{p}.{name}.weight, multiply_model.py:81-92,
+    body_model_params.py:5-50) override the directory's poses the way the opt_smpl branch does (:163-170)."""
+    _make_dir(tmp_path, F=4, P=2)
+    seq = D.SequenceData(str(tmp_path))
+    g = torch.Generator().manual_seed(0)
+    sd = {"model.density.beta": torch.tensor(0.1)}
+    for p in range(2):
+        sd["body_model_list.%d.betas.weight" % p] = torch.randn(1, 10, generator=g)
+        sd["body_model_list.%d.global_orient.weight" % p] = torch.randn(4, 3, generator=g)
+        sd["body_model_list.%d.body_pose.weight" % p] = torch.randn(4, 69, generator=g)
+        sd["body_model_list.%d.transl.weight" % p] = torch.randn(4, 3, generator=g)
+    bp = D.body_params_from_state_dict(sd)
+    assert len(bp) == 2 and bp[1]["body_pose"].shape == (4, 69)
+    plain = seq.frame(2)
+    opt = seq.frame(2, body_params=bp)
+    assert opt["smpl_pose"].shape == (1, 2, 72) and opt["smpl_shape"].shape == (1, 2, 10) and opt["smpl_trans"].shape == (1, 2, 3)
+    for p in range(2):
+        assert torch.equal(opt["smpl_pose"][0, p, :3], sd["body_model_list.%d.global_orient.weight" % p][2])
+        assert torch.equal(opt["smpl_pose"][0, p, 3:], sd["body_model_list.%d.body_pose.weight" % p][2])
+        assert torch.equal(opt["smpl_trans"][0, p], sd["body_model_list.%d.transl.weight" % p][2])
+        assert torch.equal(opt["smpl_shape"][0, p], sd["body_model_list.%d.betas.weight" % p][0])
+    assert torch.equal(opt["smpl_params"], plain["smpl_params"]) and torch.equal(opt["uv"], plain["uv"])   # scale etc. unchanged
+    assert not torch.equal(opt["smpl_pose"], plain["smpl_pose"])
+    assert D.body_params_from_state_dict({"model.density.beta": torch.tensor(0.1)}) == []
+    del sd["body_model_list.1.transl.weight"]
+    with pytest.raises(KeyError):
+        D.body_params_from_state_dict(sd)
