@@ -58,3 +58,32 @@ def test_product_path_has_no_oracle_import():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, f
+
+
+def test_quaternion_pose_form():
+    """rend_util.get_camera_params accepts pose as [B,7] = quaternion (w,x,y,z) | centre (rend_util.py:46-50, quat_to_rot
+    :88-105): the mirror expands it to the same matrix scipy's Rotation gives, and the host ray builder agrees with the
+    matrix form."""
+    import numpy as np
+    import torch
+    from scipy.spatial.transform import Rotation
+    from multiply_b200.model import rend_util
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal((5, 4))
+    c = rng.standard_normal((5, 3))
+    pose7 = torch.tensor(np.concatenate([q * 3.0, c], 1), dtype=torch.float32)        # un-normalised on purpose
+    M = rend_util.pose_matrix(pose7)
+    qn = q / np.linalg.norm(q, axis=1, keepdims=True)
+    R = Rotation.from_quat(qn[:, [1, 2, 3, 0]]).as_matrix()                            # scipy wants x,y,z,w
+    assert np.allclose(M[:, :3, :3].numpy(), R, atol=1e-6)
+    assert np.allclose(M[:, :3, 3].numpy(), c, atol=1e-7)
+    assert np.allclose(M[:, 3].numpy(), np.tile([0, 0, 0, 1.0], (5, 1)))
+    m44 = torch.eye(4)[None]
+    assert rend_util.pose_matrix(m44) is m44
+    K = torch.eye(4)[None].clone()
+    K[0, 0, 0] = K[0, 1, 1] = 500.0
+    K[0, 0, 2] = K[0, 1, 2] = 128.0
+    uv = torch.tensor(rng.random((1, 7, 2)) * 256, dtype=torch.float32)
+    d7, c7 = rend_util.get_camera_params_host(uv, pose7[:1], K)
+    d4, c4 = rend_util.get_camera_params_host(uv, M[:1], K)
+    assert torch.equal(d7, d4) and torch.equal(c7, c4)
