@@ -162,6 +162,8 @@ class Multiply(nn.Module):
         networks still comes from ``smpl_pose`` (:270).  No host synchronisation happens on this path when the SMPL
         servers live on the device (model.smpl.SMPLServer): SMPL forward, culling, sampling, MLPs and compositing
         are all enqueued asynchronously."""
+        if input["pose"].dim() == 2:            # [1,7] quaternion | centre form (rend_util.py:46-50) -> [1,4,4]
+            input = dict(input, pose=rend_util.pose_matrix(input["pose"]))
         if self.training:
             return self._forward_train_values(input, id, cond_zero_shit)
         dev = input["uv"].device
